@@ -1,0 +1,169 @@
+"""Pins oracle/cos_oracle.py to fixtures produced by the unmodified reference (tests/golden/make_golden.py).
+
+The oracle is NumPy on the same libm as the reference, written in the reference's operation order, so
+the scalar restatement is expected to be bit-identical and the vectorised one within a few ulp.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import cos_oracle as O
+
+SCALAR_TOL = 1e-15      # scalar restatement: same operations in the same order
+# vectorised restatement: NumPy's array loops for complex multiply are SIMD/FMA-dispatched while the
+# scalar path is not, so a few prices move by some ulp of sum|summands| (measured here: max 3.4e-13
+# relative, median 1e-15, 28 % bit-identical on 2 250 prices; SURVEY §8c measured 1.0e-13)
+VEC_TOL = 1e-12
+
+
+def test_survey_literals_are_tripwires(golden):
+    """SURVEY.md §8c known-answer literals, recomputed by the reference into known_answers.npz."""
+    g = golden("known_answers.npz")
+    lit = np.array([[12.747652821906351, 9.173273829175123, 6.24553807185953, 4.007886084802539, 2.420075396920669],
+                    [15.270182516467568, 11.972625306950297, 9.14571864274245, 6.803206414460713, 4.928582339601269],
+                    [19.314600566413443, 16.2638895064355, 13.545233402249403, 11.1599576440257, 9.099103247472208]])
+    assert np.array_equal(g["prices"], lit)
+    assert np.array_equal(g["ab"], np.array([(-1.4132777861296757, 1.4432777861296755),
+                                              (-1.9993873329093776, 2.0593873329093775),
+                                              (-2.8282625135277004, 2.9482625135277005)]))
+    assert float(g["demo_call"]) == 13.872851144174323
+    assert float(g["demo_put"]) == 8.995793594010637
+
+
+def test_scalar_oracle_known_answers(golden):
+    g = golden("known_answers.npz")
+    for i, T in enumerate(g["maturities"]):
+        for j, K in enumerate(g["strikes"]):
+            got = O.price_scalar(g["params"], 100.0, float(K), float(T), 0.05)
+            assert rel_err(got, g["prices"][i, j]) <= SCALAR_TOL
+        a, b = O.truncation_range_scalar(g["params"], 100.0, 100.0, float(T), 0.05)
+        assert (a, b) == tuple(g["ab"][i])
+    assert rel_err(O.price_scalar(g["demo_params"], 100, 100, 1.0, 0.05, True), g["demo_call"]) <= SCALAR_TOL
+    assert rel_err(O.price_scalar(g["demo_params"], 100, 100, 1.0, 0.05, False), g["demo_put"]) <= SCALAR_TOL
+
+
+def test_scalar_oracle_grid_sample(golden):
+    g = golden("prices_grid15.npz")
+    worst = 0.0
+    for p in range(0, 150, 15):
+        for i, T in enumerate(g["maturities"]):
+            for j, kr in enumerate(g["k_rel"]):
+                K = kr * g["spots"][p] / 100.0
+                got = O.price_scalar(g["params"][p], g["spots"][p], K, float(T), float(g["r"]))
+                worst = max(worst, float(rel_err(got, g["prices"][p, i, j])))
+    assert worst <= SCALAR_TOL, worst
+
+
+def test_vector_oracle_grid15(golden):
+    g = golden("prices_grid15.npz")
+    strikes = g["k_rel"][None, :] * g["spots"][:, None] / 100.0                  # [P,5]
+    K = np.tile(strikes, (1, 3))                                                 # maturity-major
+    T = np.repeat(g["maturities"], 5)
+    got, ab = O.price_batch(g["params"], g["spots"], K, T, np.ones(15), float(g["r"]), return_ab=True)
+    err = rel_err(got.reshape(150, 3, 5), g["prices"])
+    assert err.max() <= VEC_TOL, err.max()
+    assert np.abs(ab.reshape(150, 3, 5, 2) - g["ab"]).max() <= 1e-14
+
+
+@pytest.mark.parametrize("tag", ["main", "edge"])
+def test_vector_oracle_dense_surface(golden, tag):
+    g = golden("dense_surface.npz")
+    Ks, Ts = g[f"{tag}_strikes"], g[f"{tag}_maturities"]
+    K = np.tile(Ks, len(Ts)); T = np.repeat(Ts, len(Ks))
+    got, ab = O.price_batch(g["params"], 100.0, K, T, np.ones(K.size), float(g["r"]), N=256, return_ab=True)
+    want = g[f"{tag}_prices"].reshape(4, -1)
+    # deep OTM short-dated prices are rounding noise: judge abs error against S0
+    assert (np.abs(got - want) / 100.0).max() <= 2e-13
+    big = np.abs(want) > 0.5        # the C3 main grid has prices >= 0.6
+    assert rel_err(got[big], want[big]).max() <= 1e-11
+    assert np.abs(ab.reshape(want.shape + (2,)) - g[f"{tag}_ab"].reshape(want.shape + (2,))).max() <= 1e-14
+
+
+def test_oracle_edge_cases(golden):
+    g = golden("edge_cases.npz")
+    n = g["prices"].shape[0]
+    assert n >= 70
+    for i in range(n):
+        S0, K, T, r, q, call, N = g["meta"][i]
+        want = g["prices"][i]
+        got_s = O.price_scalar(g["params"][i], S0, K, T, r, bool(call), q, int(N))
+        got_v = O.price_batch(g["params"][i], S0, [K], [T], [call], r, q, int(N))[0, 0]
+        if np.isnan(want):
+            assert np.isnan(got_s) and np.isnan(got_v)
+            continue
+        assert rel_err(got_s, want) <= 1e-13 or abs(got_s - want) <= 1e-13 * S0, (i, got_s, want)
+        assert abs(got_v - want) <= 5e-13 * max(S0, K), (i, got_v, want)
+        a, b = O.truncation_range_scalar(g["params"][i], S0, K, T, r)
+        assert np.allclose([a, b], g["ab"][i], rtol=1e-15, atol=0, equal_nan=True)
+
+
+def test_oracle_cf(golden):
+    g = golden("cf_values.npz")
+    P, nT, nU = g["cf"].shape
+    for p in range(P):
+        for i, tau in enumerate(g["taus"]):
+            vec = O.cf_vec(g["us"][None, :], np.array([[tau]]), g["params"][p][None, :], float(g["r"]), float(g["q"]))[0]
+            for j, u in enumerate(g["us"]):
+                s = O.cf_scalar(u, tau, g["params"][p], float(g["r"]), float(g["q"]))
+                want = g["cf"][p, i, j]
+                assert abs(s - want) <= 1e-15 * abs(want)
+                assert abs(vec[j] - want) <= 1e-13 * abs(want)
+    assert np.all(g["cf"][:, :, 0] == 1.0)          # phi(0) = 1 exactly
+
+
+@pytest.mark.parametrize("tag", ["c1", "ragged"])
+def test_oracle_loss_and_fd(golden, tag):
+    g = golden("loss_cases.npz")
+    m = (float(g[f"{tag}_spot"]), float(g[f"{tag}_r"]), g[f"{tag}_strike"], g[f"{tag}_maturity"],
+         g[f"{tag}_is_call"], g[f"{tag}_market"])
+    got = O.loss_batch(g[f"{tag}_x"], *m)
+    want = g[f"{tag}_loss"]
+    assert np.array_equal(got == O.SENTINEL, want == 1e10)
+    assert (want == 1e10).sum() >= 2                      # NaN / inf parameter cases hit the sentinel
+    assert (want > 100).sum() >= 3                        # Feller penalty active
+    assert np.abs(got - want).max() <= 1e-9               # north-star bound
+    # far tighter in practice (the loss at the true parameters is ~1e-28, i.e. pure rounding noise)
+    assert np.all(np.abs(got - want) <= 1e-13 + 1e-11 * np.abs(want))
+    # scalar path on a few
+    for i in (0, 5, 27, 30):
+        assert rel_err(O.loss_scalar(g[f"{tag}_x"][i], *m), want[i]) <= 1e-13
+    # finite-difference stencil and gradient rule
+    for c in range(g[f"{tag}_fd_f"].shape[0]):
+        pts, dx = O.fd_stencil(g[f"{tag}_x"][c])
+        f = O.loss_batch(pts, *m)
+        assert np.abs(f - g[f"{tag}_fd_f"][c]).max() <= 1e-12
+        f0, grad = O.loss_fd(g[f"{tag}_x"][c], *m)
+        # forward differences with h=1e-8 turn ~1e-15 loss rounding noise into ~1e-7 gradient
+        # noise: that noise floor, not an algorithmic difference, is the bound here
+        noise = (1e-13 * abs(f0) + 1e-15) / O.FD_STEP
+        assert np.abs(grad - g[f"{tag}_fd_g"][c]).max() <= noise
+
+
+def test_oracle_initial_guess(golden):
+    g = golden("initial_guess.npz")
+    np.random.seed(0)
+    m = (float(g["spot"]), g["strike"], g["maturity"], g["market"])
+    assert np.array_equal(O.initial_guess(0, *m), g["g0"])
+    assert np.array_equal(O.initial_guess(1, *m), g["g1"])
+    assert np.array_equal(O.initial_guess(2, *m), g["g2"])
+    assert np.array_equal(O.initial_guess(1, *m), g["g1_second_draw"])
+    # f(x0) literals for the C1 market
+    assert float(g["f_g0"]) == 9.7610424427883e-05
+    assert float(g["f_g1"]) == 11.100198535727506
+
+
+def test_oracle_generator_draws(golden):
+    g = golden("generator_seed42.npz")
+    np.random.seed(42)
+    params, spots, noise = O.generator_draws(20)
+    assert np.array_equal(params, g["params"])
+    assert np.array_equal(spots, g["spots"])
+    K = O.GENERATOR_STRIKES_REL[None, :] * spots[:, None] / 100.0
+    K = np.tile(K, (1, 3)); T = np.repeat(O.GENERATOR_MATURITIES, 5)
+    assert np.array_equal(K, g["strikes"]) and np.array_equal(np.tile(T, (20, 1)), g["maturities"])
+    model = O.price_batch(params, spots, K, T, np.ones(15), O.GENERATOR_RATE)
+    assert rel_err(model, g["model_prices"]).max() <= VEC_TOL
+    market = g["model_prices"] + noise * g["model_prices"]         # synthetic_generator.py:141-142
+    assert np.array_equal(market, g["market_prices"])
+    # SURVEY §8c literal
+    assert g["model_prices"][0, 0] == 12.426829764997922
