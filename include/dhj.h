@@ -1,0 +1,143 @@
+/* dhj.h — C ABI of libdhj.so: B200 (sm_100a) COS pricing of the Double-Heston + Merton-jump model.
+ *
+ * This is the drop-in boundary for the ONE hot path this repository accelerates.  The reference
+ * (zenthepen/Option-Pricing-FFN-LBFGS, mounted at /root/reference while building) is pure Python and
+ * has no FFI of its own; its boundary is the Python API of three modules.  Each entry point below
+ * names the reference interface it replaces (file:line under /root/reference); INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every array is C-contiguous float64 (or int32 where said), owned by
+ *     the caller and only read/written during the call; the library owns its device scratch, pinned
+ *     staging buffers and streams;
+ *   - the 13 model parameters are always in calibrator order (src/calibration/lbfgs_calibrator.py:53-57):
+ *       v01, kappa1, theta1, sigma1, rho1, v02, kappa2, theta2, sigma2, rho2, lambda_j, mu_j, sigma_j
+ *   - every function returns 0 on success or a negative DHJ_ERR_* code and never throws; the text of the
+ *     last error is available from dhj_last_error();
+ *   - a context is bound to one CUDA device; calls on one context must be serialised by the caller
+ *     (the reference is single-threaded: SURVEY §8b);
+ *   - there is no CPU fallback: without a CUDA device dhj_init fails with DHJ_ERR_CUDA.
+ *   - `*_dev` entry points take CUDA DEVICE pointers and a cudaStream_t (passed as void*), enqueue the
+ *     work and return without synchronising; they exist so that callers that already hold data in HBM
+ *     (bench.py's kernel-only arm, a torch pipeline) skip the host copies.
+ */
+#ifndef DHJ_H_
+#define DHJ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DHJ_ABI_VERSION 1
+#define DHJ_N_PARAMS 13
+
+#define DHJ_OK 0
+#define DHJ_ERR_ARG (-1)     /* bad argument (null pointer, non-positive size, N < 1 ...) */
+#define DHJ_ERR_CUDA (-2)    /* CUDA runtime error, no device, wrong architecture */
+#define DHJ_ERR_NOMEM (-3)   /* host or device allocation failed */
+
+#if defined(__GNUC__)
+#define DHJ_API __attribute__((visibility("default")))
+#else
+#define DHJ_API
+#endif
+
+typedef struct dhj_ctx dhj_ctx;
+typedef struct dhj_market dhj_market;
+
+/* ---- context -------------------------------------------------------------------------------- */
+DHJ_API int dhj_abi_version(void);
+DHJ_API int dhj_device_count(int* count);
+DHJ_API int dhj_init(int device, dhj_ctx** ctx);
+DHJ_API int dhj_destroy(dhj_ctx* ctx);
+/* text of the last error on `ctx` (or of the last failed dhj_init when ctx is NULL); never NULL */
+DHJ_API const char* dhj_last_error(const dhj_ctx* ctx);
+/* number of kernels this context has launched since dhj_init (bench.py's gpu_launches) */
+DHJ_API int dhj_launch_count(const dhj_ctx* ctx, int64_t* count);
+
+/* ---- pricing -------------------------------------------------------------------------------- */
+/* Replaces P x M constructions of DoubleHeston(S0,K,T,r,<13 params>,option_type,q).pricing(N)
+ * (src/models/double_heston.py:26-46, 160-192) on an arbitrary option LIST.
+ *   params[P][13]; S0: s0_stride==0 -> one spot S0[0] for all sets, ==1 -> S0[P];
+ *   strike: strike_stride==0 -> strike[M] shared, ==M -> strike[P][M]; maturity[M];
+ *   is_call[M] (1 = call, 0 = put: the reference's first-letter rule double_heston.py:172 is applied
+ *   by the Python host); N >= 1 cosine terms; L = truncation multiplier (reference default 10,
+ *   double_heston.py:100); out[P][M].  Options are grouped by maturity internally; a strike whose
+ *   +-0.1 widening binds (double_heston.py:135-137) gets its own truncation range exactly as in the
+ *   reference. */
+DHJ_API int dhj_price_list(dhj_ctx* ctx, const double* params, int64_t P, const double* S0, int64_t s0_stride,
+                   double r, double q, const double* strike, int64_t strike_stride, const double* maturity,
+                   const int32_t* is_call, int32_t M, int32_t N, double L, double* out);
+
+/* Grid fast path, output maturity-major out[P][nT][nK] like the generator's loop
+ * (src/data/synthetic_generator.py:123-138).  scale_by_spot != 0 -> K = strikes[j]*S0/100
+ * (synthetic_generator.py:125), else K = strikes[j]. */
+DHJ_API int dhj_price_grid(dhj_ctx* ctx, const double* params, int64_t P, const double* S0, int64_t s0_stride,
+                   double r, double q, const double* strikes, int32_t nK, const double* maturities,
+                   int32_t nT, int32_t scale_by_spot, int32_t is_call, int32_t N, double L, double* out);
+
+/* Same, with params / S0 / out already in device memory; strikes and maturities are host arrays
+ * (tiny tables).  Asynchronous on `stream` (a cudaStream_t; NULL = CUDA's default stream, which is
+ * what `torch.cuda.current_stream().cuda_stream` is unless the caller changed it). */
+DHJ_API int dhj_price_grid_dev(dhj_ctx* ctx, const double* d_params, int64_t P, const double* d_S0,
+                       int64_t s0_stride, double r, double q, const double* strikes, int32_t nK,
+                       const double* maturities, int32_t nT, int32_t scale_by_spot, int32_t is_call,
+                       int32_t N, double L, double* d_out, void* stream);
+
+/* ---- calibration loss ----------------------------------------------------------------------- */
+/* A market = what DoubleHestonJumpCalibrator.__init__ stores (src/calibration/lbfgs_calibrator.py:47-60):
+ * spot, risk-free rate and the option list (strike, maturity, price, type).  `n_markets` markets that
+ * share maturities / option types can be held in one object (one per calibration instance when many
+ * calibrations are batched): S0[n_markets]; strike[n_markets][M] (strike_stride = M) or strike[M]
+ * (strike_stride = 0); maturity[M]; is_call[M]; price[n_markets][M].  N is the COS size used by the
+ * loss (the reference always uses 128: lbfgs_calibrator.py:150). */
+DHJ_API int dhj_market_create(dhj_ctx* ctx, int32_t n_markets, int32_t M, const double* S0, double r,
+                      const double* strike, int64_t strike_stride, const double* maturity,
+                      const int32_t* is_call, const double* price, int32_t N, dhj_market** market);
+DHJ_API int dhj_market_destroy(dhj_market* market);
+
+/* compute_loss(x) for B unconstrained vectors x[B][13] (lbfgs_calibrator.py:118-177): exp/tanh
+ * transform (:62-87), prices of every option, 1e10 if any price is NaN/inf/<=0 (:152-153), else
+ * mean(((model-market)/market)^2) + Feller penalty (:111-116, :163-169).  market_index[B] selects
+ * the market of each vector (NULL -> market 0).  out_loss[B]. */
+DHJ_API int dhj_loss_batch(dhj_ctx* ctx, const dhj_market* market, const double* x, const int32_t* market_index,
+                   int64_t B, double* out_loss);
+
+/* One launch for what scipy's L-BFGS-B asks per step with jac=None: f(x) and the 13 forward
+ * differences g_i = (f(x + h e_i) - f(x)) / ((x_i + h) - x_i)  (scipy/optimize/_numdiff.py
+ * _dense_difference, '2-point', abs_step = h; called from lbfgs_calibrator.py:259-269), for C
+ * optimiser states x[C][13] at once.  The 14 variants are built on the device.
+ * out_f[C], out_g[C][13]; out_f_all (optional, may be NULL) receives the 14 losses [C][14] in
+ * evaluation order (f(x), f(x+h e_0), ...), which the host needs to keep the reference's
+ * `best_loss` / `n_calls` bookkeeping (lbfgs_calibrator.py:120, 171-172). */
+DHJ_API int dhj_loss_fd(dhj_ctx* ctx, const dhj_market* market, const double* x, const int32_t* market_index,
+                int64_t C, double h, double* out_f, double* out_g, double* out_f_all);
+
+/* Model prices of every market option at the transformed x (calibrate()'s re-pricing at the optimum,
+ * lbfgs_calibrator.py:274-299).  out_prices[B][M] in the caller's option order. */
+DHJ_API int dhj_market_prices(dhj_ctx* ctx, const dhj_market* market, const double* x, const int32_t* market_index,
+                      int64_t B, double* out_prices);
+
+/* ---- the remaining public methods of DoubleHeston ------------------------------------------- */
+/* characteristic_function(phi, tau) at n real frequencies u[n] (double_heston.py:48-97). */
+DHJ_API int dhj_cf(dhj_ctx* ctx, const double* params, double r, double q, double tau, const double* u, int32_t n,
+           double* out_re, double* out_im);
+/* truncationRange(L): (a,b) for P sets x M options, out_ab[P][M][2] (double_heston.py:100-139). */
+DHJ_API int dhj_truncation_range(dhj_ctx* ctx, const double* params, int64_t P, const double* S0, int64_t s0_stride,
+                         double r, const double* strike, const double* maturity, int32_t M, double L,
+                         double* out_ab);
+/* chi_k(k,c,d,a,b) and psi_k(k,c,d,a,b) for n integers k[n] (double_heston.py:141-158). */
+DHJ_API int dhj_chi_psi(dhj_ctx* ctx, const int32_t* k, int32_t n, double c, double d, double a, double b,
+                double* out_chi, double* out_psi);
+
+/* ---- measurement ---------------------------------------------------------------------------- */
+/* Runs a register-resident FP64 FMA-chain kernel on every SM and reports the sustained DFMA rate
+ * (2 flop per FMA) — the denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 figure). */
+DHJ_API int dhj_fp64_peak(dhj_ctx* ctx, int32_t iters, double* tflops, double* milliseconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DHJ_H_ */

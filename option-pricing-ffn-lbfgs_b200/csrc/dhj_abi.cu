@@ -1,0 +1,744 @@
+// dhj_abi.cu — host side of libdhj.so: contexts, device/pinned buffers, option books, and the extern "C"
+// entry points declared in include/dhj.h.  No torch, no Python: plain CUDA runtime.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "dhj.h"
+#include "dhj_kernels.cuh"
+
+using namespace dhj;
+
+namespace {
+
+char g_init_error[512] = "";
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = std::max(bytes, (size_t)256);
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Host description of the option slices (options grouped by maturity, first-appearance order).
+struct BookHost {
+  int M = 0, n_slices = 0;
+  std::vector<double> slice_T;
+  std::vector<int> slice_off, pos;
+  std::vector<unsigned char> call;
+  std::vector<double> strike;   // caller order; rows * M (or M when shared)
+  void group(const double* maturity, const int32_t* is_call, int m) {
+    M = m;
+    slice_T.clear();
+    std::vector<int> slice_of(m);
+    for (int o = 0; o < m; ++o) {
+      int s = -1;
+      for (size_t t = 0; t < slice_T.size(); ++t)
+        if (slice_T[t] == maturity[o] || (std::isnan(slice_T[t]) && std::isnan(maturity[o]))) { s = (int)t; break; }
+      if (s < 0) { s = (int)slice_T.size(); slice_T.push_back(maturity[o]); }
+      slice_of[o] = s;
+    }
+    n_slices = (int)slice_T.size();
+    slice_off.assign(n_slices + 1, 0);
+    for (int o = 0; o < m; ++o) slice_off[slice_of[o] + 1]++;
+    for (int s = 0; s < n_slices; ++s) slice_off[s + 1] += slice_off[s];
+    pos.assign(m, 0); call.assign(m, 0);
+    std::vector<int> fill(slice_off.begin(), slice_off.end() - 1);
+    for (int o = 0; o < m; ++o) {
+      int d = fill[slice_of[o]]++;
+      pos[d] = o;
+      call[d] = is_call[o] ? 1 : 0;
+    }
+  }
+  void grid(const double* maturities, int nT, int nK, int is_call_flag) {
+    M = nT * nK; n_slices = nT;
+    slice_T.assign(maturities, maturities + nT);
+    slice_off.resize(nT + 1);
+    for (int t = 0; t <= nT; ++t) slice_off[t] = t * nK;
+    pos.resize(M); call.assign(M, is_call_flag ? 1 : 0);
+    for (int o = 0; o < M; ++o) pos[o] = o;
+  }
+  // bytes of the packed device image: slice_T | slice_off | pos | call (8-byte aligned segments)
+  size_t packed_bytes() const {
+    return align8(n_slices * sizeof(double)) + align8((n_slices + 1) * sizeof(int)) + align8(M * sizeof(int)) +
+           align8(M);
+  }
+  static size_t align8(size_t b) { return (b + 7) & ~(size_t)7; }
+  void pack(unsigned char* dst) const {
+    size_t o = 0;
+    memcpy(dst + o, slice_T.data(), n_slices * sizeof(double)); o += align8(n_slices * sizeof(double));
+    memcpy(dst + o, slice_off.data(), (n_slices + 1) * sizeof(int)); o += align8((n_slices + 1) * sizeof(int));
+    memcpy(dst + o, pos.data(), M * sizeof(int)); o += align8(M * sizeof(int));
+    memcpy(dst + o, call.data(), M);
+  }
+  void view(SliceView* v, const unsigned char* dbase) const {
+    size_t o = 0;
+    v->n_slices = n_slices; v->n_options = M;
+    v->slice_T = (const double*)(dbase + o); o += align8(n_slices * sizeof(double));
+    v->slice_off = (const int*)(dbase + o); o += align8((n_slices + 1) * sizeof(int));
+    v->pos = (const int*)(dbase + o); o += align8(M * sizeof(int));
+    v->call = dbase + o;
+  }
+};
+
+constexpr int kSlots = 2;
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  DevBuf d_in, d_out;
+  PinBuf h_in, h_out;
+  // deferred copy-out of a staged chunk
+  double* user_out = nullptr;
+  size_t out_bytes = 0;
+  bool pending = false;
+};
+
+}  // namespace
+
+struct dhj_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int price_blocks_per_sm = 1;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  char err[512] = "";
+  // cached option book for the pricing entry points
+  DevBuf d_book, d_tables;
+  PinBuf h_book;
+  std::vector<unsigned char> book_image;      // last uploaded packed image (+ strike table) for reuse
+  Slot slots[kSlots];
+  // loss path
+  DevBuf d_x, d_idx, d_f, d_fg, d_counters, d_prices;
+  PinBuf h_x, h_res;
+  size_t counters_zeroed = 0;
+  DevBuf d_peak;
+};
+
+struct dhj_market {
+  dhj_ctx* ctx = nullptr;
+  int n_markets = 0, M = 0, N = 128;
+  double r = 0.0;
+  BookHost book;
+  DevBuf d_book, d_strike, d_S0, d_price;
+  long long strike_stride = 0;
+  SliceView view{};
+};
+
+namespace {
+
+int fail(dhj_ctx* ctx, int code, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_init_error;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define DHJ_CUDA(ctx, call)                                                                          \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail((ctx), e__ == cudaErrorMemoryAllocation ? DHJ_ERR_NOMEM : DHJ_ERR_CUDA,            \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);     \
+  } while (0)
+
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+int price_grid_blocks(const dhj_ctx* ctx, long long items) {
+  long long want = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  long long cap = (long long)ctx->sm_count * ctx->price_blocks_per_sm;
+  return (int)std::max<long long>(1, std::min(want, cap));
+}
+
+// Upload (or reuse) the packed book image + shared strike table for a pricing call on `stream`.
+int upload_book(dhj_ctx* ctx, const BookHost& book, const double* shared_strikes, int n_shared,
+                cudaStream_t stream, SliceView* v) {
+  const size_t bb = book.packed_bytes();
+  const size_t sb = BookHost::align8((size_t)n_shared * sizeof(double));
+  std::vector<unsigned char> image(bb + sb);
+  book.pack(image.data());
+  if (n_shared) memcpy(image.data() + bb, shared_strikes, (size_t)n_shared * sizeof(double));
+  if (image != ctx->book_image) {
+    // the pinned staging area may still feed an earlier asynchronous upload
+    DHJ_CUDA(ctx, cudaDeviceSynchronize());
+    DHJ_CUDA(ctx, ctx->d_book.reserve(image.size()));
+    DHJ_CUDA(ctx, ctx->h_book.reserve(image.size()));
+    memcpy(ctx->h_book.p, image.data(), image.size());
+    DHJ_CUDA(ctx, cudaMemcpyAsync(ctx->d_book.p, ctx->h_book.p, image.size(), cudaMemcpyHostToDevice, stream));
+    // later calls may use other streams: make the table visible to all of them
+    DHJ_CUDA(ctx, cudaStreamSynchronize(stream));
+    ctx->book_image.swap(image);
+  }
+  book.view(v, (const unsigned char*)ctx->d_book.p);
+  v->strike = n_shared ? (const double*)((const unsigned char*)ctx->d_book.p + bb) : nullptr;
+  v->strike_stride = 0;
+  return DHJ_OK;
+}
+
+int check_common(dhj_ctx* ctx, const void* params, int64_t P, const void* S0, int32_t N, double L, const void* out) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  if (!params || !S0 || !out) return fail(ctx, DHJ_ERR_ARG, "null array argument");
+  if (P < 0) return fail(ctx, DHJ_ERR_ARG, "P must be >= 0 (got %lld)", (long long)P);
+  if (N < 1) return fail(ctx, DHJ_ERR_ARG, "N must be >= 1 (got %d)", N);
+  if (!(L == L)) return fail(ctx, DHJ_ERR_ARG, "L is NaN");
+  return DHJ_OK;
+}
+
+// Chunked, double-buffered host-to-host pricing: params/S0/strike rows in, price rows out.
+int run_price_host(dhj_ctx* ctx, SliceView v, const double* params, int64_t P, const double* S0,
+                   int64_t s0_stride, const double* strike, int64_t strike_stride, double* out) {
+  const int M = v.n_options;
+  if (P == 0 || M == 0) return DHJ_OK;
+  const size_t in_row = (size_t)kNumParams + (s0_stride ? 1 : 0) + (strike_stride ? (size_t)M : 0);
+  const size_t row_doubles = in_row + (size_t)M;
+  int64_t chunk = (int64_t)std::max<size_t>(256, std::min<size_t>(131072, ((size_t)1 << 23) / row_doubles));
+  chunk = std::min<int64_t>(chunk, P);
+  const bool pin_in = is_pinned_host(params) && (!s0_stride || is_pinned_host(S0)) &&
+                      (!strike_stride || is_pinned_host(strike));
+  const bool pin_out = is_pinned_host(out);
+  int slot_i = 0;
+  for (int64_t lo = 0; lo < P; lo += chunk, slot_i ^= 1) {
+    const int64_t n = std::min<int64_t>(chunk, P - lo);
+    Slot& sl = ctx->slots[slot_i];
+    // the slot's previous chunk must have left its buffers
+    DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));
+    if (sl.pending) { memcpy(sl.user_out, sl.h_out.p, sl.out_bytes); sl.pending = false; }
+    const size_t pb = (size_t)n * kNumParams * sizeof(double);
+    const size_t s0b = s0_stride ? (size_t)n * sizeof(double) : sizeof(double);
+    const size_t kb = strike_stride ? (size_t)n * M * sizeof(double) : 0;
+    const size_t ob = (size_t)n * M * sizeof(double);
+    DHJ_CUDA(ctx, sl.d_in.reserve(pb + s0b + kb));
+    DHJ_CUDA(ctx, sl.d_out.reserve(ob));
+    unsigned char* din = (unsigned char*)sl.d_in.p;
+    const double* src_params = params + lo * kNumParams;
+    const double* src_s0 = s0_stride ? S0 + lo : S0;
+    const double* src_strike = strike_stride ? strike + lo * (int64_t)M : nullptr;
+    if (pin_in) {
+      DHJ_CUDA(ctx, cudaMemcpyAsync(din, src_params, pb, cudaMemcpyHostToDevice, sl.stream));
+      DHJ_CUDA(ctx, cudaMemcpyAsync(din + pb, src_s0, s0b, cudaMemcpyHostToDevice, sl.stream));
+      if (kb) DHJ_CUDA(ctx, cudaMemcpyAsync(din + pb + s0b, src_strike, kb, cudaMemcpyHostToDevice, sl.stream));
+    } else {
+      DHJ_CUDA(ctx, sl.h_in.reserve(pb + s0b + kb));
+      unsigned char* hin = (unsigned char*)sl.h_in.p;
+      memcpy(hin, src_params, pb);
+      memcpy(hin + pb, src_s0, s0b);
+      if (kb) memcpy(hin + pb + s0b, src_strike, kb);
+      DHJ_CUDA(ctx, cudaMemcpyAsync(din, hin, pb + s0b + kb, cudaMemcpyHostToDevice, sl.stream));
+    }
+    SliceView vv = v;
+    if (strike_stride) { vv.strike = (const double*)(din + pb + s0b); vv.strike_stride = M; }
+    PriceArgs a;
+    a.params = (const double*)din; a.S0 = (const double*)(din + pb); a.s0_stride = s0_stride ? 1 : 0;
+    a.row_index = nullptr; a.P = n; a.transform = 0; a.out = (double*)sl.d_out.p;
+    const int blocks = price_grid_blocks(ctx, n * (long long)vv.n_slices);
+    k_price<<<blocks, kThreadsPerBlock, 0, sl.stream>>>(vv, a);
+    DHJ_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    double* dst = out + lo * (int64_t)M;
+    if (pin_out) {
+      DHJ_CUDA(ctx, cudaMemcpyAsync(dst, sl.d_out.p, ob, cudaMemcpyDeviceToHost, sl.stream));
+    } else {
+      DHJ_CUDA(ctx, sl.h_out.reserve(ob));
+      DHJ_CUDA(ctx, cudaMemcpyAsync(sl.h_out.p, sl.d_out.p, ob, cudaMemcpyDeviceToHost, sl.stream));
+      sl.user_out = dst; sl.out_bytes = ob; sl.pending = true;
+    }
+    DHJ_CUDA(ctx, cudaEventRecord(sl.done, sl.stream));
+  }
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& sl = ctx->slots[i];
+    DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));
+    if (sl.pending) { memcpy(sl.user_out, sl.h_out.p, sl.out_bytes); sl.pending = false; }
+  }
+  return DHJ_OK;
+}
+
+int stage_x(dhj_ctx* ctx, const dhj_market* mk, const double* x, const int32_t* market_index, int64_t B,
+            const int** d_index) {
+  if (!ctx || !mk) return fail(ctx, DHJ_ERR_ARG, "null context or market");
+  if (mk->ctx != ctx) return fail(ctx, DHJ_ERR_ARG, "market belongs to another context");
+  if (!x) return fail(ctx, DHJ_ERR_ARG, "null x");
+  if (B < 0 || B > (int64_t)100000000) return fail(ctx, DHJ_ERR_ARG, "bad batch size %lld", (long long)B);
+  const size_t xb = (size_t)B * kNumParams * sizeof(double);
+  const size_t ib = market_index ? (size_t)B * sizeof(int) : 0;
+  if (market_index)
+    for (int64_t i = 0; i < B; ++i)
+      if (market_index[i] < 0 || market_index[i] >= mk->n_markets)
+        return fail(ctx, DHJ_ERR_ARG, "market_index[%lld] = %d out of range [0,%d)", (long long)i,
+                    market_index[i], mk->n_markets);
+  DHJ_CUDA(ctx, ctx->h_x.reserve(xb + ib));
+  DHJ_CUDA(ctx, ctx->d_x.reserve(xb + ib));
+  memcpy(ctx->h_x.p, x, xb);
+  if (ib) memcpy((unsigned char*)ctx->h_x.p + xb, market_index, ib);
+  DHJ_CUDA(ctx, cudaMemcpyAsync(ctx->d_x.p, ctx->h_x.p, xb + ib, cudaMemcpyHostToDevice, ctx->stream));
+  *d_index = ib ? (const int*)((unsigned char*)ctx->d_x.p + xb) : nullptr;
+  return DHJ_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int dhj_abi_version(void) { return DHJ_ABI_VERSION; }
+
+int dhj_device_count(int* count) {
+  if (!count) return fail(nullptr, DHJ_ERR_ARG, "null count");
+  cudaError_t e = cudaGetDeviceCount(count);
+  if (e != cudaSuccess) {
+    *count = 0;
+    cudaGetLastError();
+    return fail(nullptr, DHJ_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+  }
+  return DHJ_OK;
+}
+
+int dhj_init(int device, dhj_ctx** out) {
+  if (!out) return fail(nullptr, DHJ_ERR_ARG, "null ctx pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(nullptr, DHJ_ERR_CUDA, "no CUDA device available (%s); libdhj has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0 || device >= n) return fail(nullptr, DHJ_ERR_ARG, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  DHJ_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, DHJ_ERR_CUDA, "device %d is sm_%d%d; libdhj is built for sm_100a (B200) only", device,
+                prop.major, prop.minor);
+  DHJ_CUDA(nullptr, cudaSetDevice(device));
+  dhj_ctx* ctx = new (std::nothrow) dhj_ctx();
+  if (!ctx) return fail(nullptr, DHJ_ERR_NOMEM, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < kSlots && e2 == cudaSuccess; ++i) {
+    e2 = cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->slots[i].done, cudaEventDisableTiming);
+    if (e2 == cudaSuccess) e2 = cudaEventRecord(ctx->slots[i].done, ctx->slots[i].stream);
+  }
+  int bps = 0;
+  if (e2 == cudaSuccess)
+    e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_price, kThreadsPerBlock, 0);
+  if (e2 != cudaSuccess) {
+    fail(nullptr, DHJ_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e2));
+    dhj_destroy(ctx);
+    return DHJ_ERR_CUDA;
+  }
+  ctx->price_blocks_per_sm = std::max(1, bps);
+  *out = ctx;
+  return DHJ_OK;
+}
+
+int dhj_destroy(dhj_ctx* ctx) {
+  if (!ctx) return DHJ_OK;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& s = ctx->slots[i];
+    s.d_in.release(); s.d_out.release(); s.h_in.release(); s.h_out.release();
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  ctx->d_book.release(); ctx->d_tables.release(); ctx->h_book.release();
+  ctx->d_x.release(); ctx->d_idx.release(); ctx->d_f.release(); ctx->d_fg.release();
+  ctx->d_counters.release(); ctx->d_prices.release(); ctx->h_x.release(); ctx->h_res.release();
+  ctx->d_peak.release();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return DHJ_OK;
+}
+
+const char* dhj_last_error(const dhj_ctx* ctx) { return ctx ? ctx->err : g_init_error; }
+
+int dhj_launch_count(const dhj_ctx* ctx, int64_t* count) {
+  if (!ctx || !count) return DHJ_ERR_ARG;
+  *count = ctx->launches;
+  return DHJ_OK;
+}
+
+// ---- pricing ---------------------------------------------------------------------------------
+int dhj_price_list(dhj_ctx* ctx, const double* params, int64_t P, const double* S0, int64_t s0_stride,
+                   double r, double q, const double* strike, int64_t strike_stride, const double* maturity,
+                   const int32_t* is_call, int32_t M, int32_t N, double L, double* out) {
+  int rc = check_common(ctx, params, P, S0, N, L, out);
+  if (rc) return rc;
+  if (M < 0) return fail(ctx, DHJ_ERR_ARG, "M must be >= 0");
+  if (M == 0 || P == 0) return DHJ_OK;
+  if (!strike || !maturity || !is_call) return fail(ctx, DHJ_ERR_ARG, "null option table");
+  if (s0_stride != 0 && s0_stride != 1) return fail(ctx, DHJ_ERR_ARG, "s0_stride must be 0 or 1");
+  if (strike_stride != 0 && strike_stride != M) return fail(ctx, DHJ_ERR_ARG, "strike_stride must be 0 or M");
+  DHJ_CUDA(ctx, cudaSetDevice(ctx->device));
+  BookHost book;
+  book.group(maturity, is_call, M);
+  SliceView v;
+  rc = upload_book(ctx, book, strike_stride ? nullptr : strike, strike_stride ? 0 : M, ctx->stream, &v);
+  if (rc) return rc;
+  v.scale_by_spot = 0; v.n_cos = N; v.r = r; v.q = q; v.L = L;
+  return run_price_host(ctx, v, params, P, S0, s0_stride, strike, strike_stride, out);
+}
+
+static int grid_view(dhj_ctx* ctx, const double* strikes, int32_t nK, const double* maturities, int32_t nT,
+                     int32_t scale_by_spot, int32_t is_call, int32_t N, double r, double q, double L,
+                     cudaStream_t stream, SliceView* v) {
+  if (nK < 1 || nT < 1) return fail(ctx, DHJ_ERR_ARG, "nK and nT must be >= 1");
+  if (!strikes || !maturities) return fail(ctx, DHJ_ERR_ARG, "null grid table");
+  BookHost book;
+  book.grid(maturities, nT, nK, is_call);
+  std::vector<double> tiled((size_t)nT * nK);
+  for (int t = 0; t < nT; ++t) memcpy(tiled.data() + (size_t)t * nK, strikes, (size_t)nK * sizeof(double));
+  int rc = upload_book(ctx, book, tiled.data(), nT * nK, stream, v);
+  if (rc) return rc;
+  v->scale_by_spot = scale_by_spot ? 1 : 0; v->n_cos = N; v->r = r; v->q = q; v->L = L;
+  return DHJ_OK;
+}
+
+int dhj_price_grid(dhj_ctx* ctx, const double* params, int64_t P, const double* S0, int64_t s0_stride,
+                   double r, double q, const double* strikes, int32_t nK, const double* maturities,
+                   int32_t nT, int32_t scale_by_spot, int32_t is_call, int32_t N, double L, double* out) {
+  int rc = check_common(ctx, params, P, S0, N, L, out);
+  if (rc) return rc;
+  if (s0_stride != 0 && s0_stride != 1) return fail(ctx, DHJ_ERR_ARG, "s0_stride must be 0 or 1");
+  DHJ_CUDA(ctx, cudaSetDevice(ctx->device));
+  SliceView v;
+  rc = grid_view(ctx, strikes, nK, maturities, nT, scale_by_spot, is_call, N, r, q, L, ctx->stream, &v);
+  if (rc) return rc;
+  if (P == 0) return DHJ_OK;
+  return run_price_host(ctx, v, params, P, S0, s0_stride, nullptr, 0, out);
+}
+
+int dhj_price_grid_dev(dhj_ctx* ctx, const double* d_params, int64_t P, const double* d_S0,
+                       int64_t s0_stride, double r, double q, const double* strikes, int32_t nK,
+                       const double* maturities, int32_t nT, int32_t scale_by_spot, int32_t is_call,
+                       int32_t N, double L, double* d_out, void* stream) {
+  int rc = check_common(ctx, d_params, P, d_S0, N, L, d_out);
+  if (rc) return rc;
+  if (s0_stride != 0 && s0_stride != 1) return fail(ctx, DHJ_ERR_ARG, "s0_stride must be 0 or 1");
+  DHJ_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;   // NULL = the default stream
+  SliceView v;
+  rc = grid_view(ctx, strikes, nK, maturities, nT, scale_by_spot, is_call, N, r, q, L, st, &v);
+  if (rc) return rc;
+  if (P == 0) return DHJ_OK;
+  PriceArgs a;
+  a.params = d_params; a.S0 = d_S0; a.s0_stride = s0_stride; a.row_index = nullptr; a.P = P; a.transform = 0;
+  a.out = d_out;
+  const int blocks = price_grid_blocks(ctx, P * (long long)v.n_slices);
+  k_price<<<blocks, kThreadsPerBlock, 0, st>>>(v, a);
+  DHJ_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return DHJ_OK;
+}
+
+// ---- calibration loss ------------------------------------------------------------------------
+int dhj_market_create(dhj_ctx* ctx, int32_t n_markets, int32_t M, const double* S0, double r,
+                      const double* strike, int64_t strike_stride, const double* maturity,
+                      const int32_t* is_call, const double* price, int32_t N, dhj_market** out) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  if (!out) return fail(ctx, DHJ_ERR_ARG, "null market pointer");
+  *out = nullptr;
+  if (n_markets < 1 || M < 1) return fail(ctx, DHJ_ERR_ARG, "n_markets and M must be >= 1");
+  if (!S0 || !strike || !maturity || !is_call || !price) return fail(ctx, DHJ_ERR_ARG, "null market array");
+  if (N < 1) return fail(ctx, DHJ_ERR_ARG, "N must be >= 1");
+  if (strike_stride != 0 && strike_stride != M) return fail(ctx, DHJ_ERR_ARG, "strike_stride must be 0 or M");
+  DHJ_CUDA(ctx, cudaSetDevice(ctx->device));
+  dhj_market* mk = new (std::nothrow) dhj_market();
+  if (!mk) return fail(ctx, DHJ_ERR_NOMEM, "out of host memory");
+  mk->ctx = ctx; mk->n_markets = n_markets; mk->M = M; mk->N = N; mk->r = r;
+  mk->strike_stride = strike_stride;
+  mk->book.group(maturity, is_call, M);
+  const size_t bb = mk->book.packed_bytes();
+  std::vector<unsigned char> image(bb);
+  mk->book.pack(image.data());
+  const size_t kbytes = (size_t)(strike_stride ? n_markets : 1) * M * sizeof(double);
+  const size_t pbytes = (size_t)n_markets * M * sizeof(double);
+  cudaError_t e = mk->d_book.reserve(bb);
+  if (e == cudaSuccess) e = mk->d_strike.reserve(kbytes);
+  if (e == cudaSuccess) e = mk->d_S0.reserve((size_t)n_markets * sizeof(double));
+  if (e == cudaSuccess) e = mk->d_price.reserve(pbytes);
+  if (e == cudaSuccess) e = cudaMemcpy(mk->d_book.p, image.data(), bb, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(mk->d_strike.p, strike, kbytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(mk->d_S0.p, S0, (size_t)n_markets * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(mk->d_price.p, price, pbytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    dhj_market_destroy(mk);
+    return fail(ctx, e == cudaErrorMemoryAllocation ? DHJ_ERR_NOMEM : DHJ_ERR_CUDA, "market upload failed: %s",
+                cudaGetErrorString(e));
+  }
+  mk->book.view(&mk->view, (const unsigned char*)mk->d_book.p);
+  mk->view.strike = (const double*)mk->d_strike.p;
+  mk->view.strike_stride = strike_stride;
+  mk->view.scale_by_spot = 0; mk->view.n_cos = N; mk->view.r = r; mk->view.q = 0.0; mk->view.L = 10.0;
+  *out = mk;
+  return DHJ_OK;
+}
+
+int dhj_market_destroy(dhj_market* mk) {
+  if (!mk) return DHJ_OK;
+  if (mk->ctx) cudaSetDevice(mk->ctx->device);
+  mk->d_book.release(); mk->d_strike.release(); mk->d_S0.release(); mk->d_price.release();
+  delete mk;
+  return DHJ_OK;
+}
+
+static int run_loss(dhj_ctx* ctx, const dhj_market* mk, const double* x, const int32_t* market_index, int64_t B,
+                    int fd, double h, double* out_f, double* out_g, double* out_f_all) {
+  const int* d_index = nullptr;
+  DHJ_CUDA(ctx, cudaSetDevice(ctx ? ctx->device : 0));
+  int rc = stage_x(ctx, mk, x, market_index, B, &d_index);
+  if (rc) return rc;
+  if (!out_f || (fd && !out_g)) return fail(ctx, DHJ_ERR_ARG, "null output");
+  if (B == 0) return DHJ_OK;
+  const int64_t n_blocks = fd ? B * kFdPoints : B;
+  if (n_blocks > 2147483647LL) return fail(ctx, DHJ_ERR_ARG, "batch too large for one launch");
+  DHJ_CUDA(ctx, ctx->d_f.reserve((size_t)n_blocks * sizeof(double)));
+  LossArgs a;
+  a.x = (const double*)ctx->d_x.p; a.market_index = d_index; a.S0 = (const double*)mk->d_S0.p;
+  a.market = (const double*)mk->d_price.p; a.fd = fd; a.h = h; a.f_all = (double*)ctx->d_f.p;
+  a.fg = nullptr; a.counters = nullptr;
+  size_t res_bytes = (size_t)B * sizeof(double);
+  if (fd) {
+    res_bytes = (size_t)B * kFdPoints * sizeof(double);
+    DHJ_CUDA(ctx, ctx->d_fg.reserve(res_bytes));
+    const size_t cb = (size_t)B * sizeof(unsigned int);
+    if (ctx->d_counters.cap < cb || ctx->counters_zeroed < cb) {
+      DHJ_CUDA(ctx, ctx->d_counters.reserve(cb));
+      DHJ_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, ctx->d_counters.cap, ctx->stream));
+      ctx->counters_zeroed = ctx->d_counters.cap;
+    }
+    a.fg = (double*)ctx->d_fg.p; a.counters = (unsigned int*)ctx->d_counters.p;
+  }
+  const int warps = std::max(1, std::min(kWarpsPerBlock, mk->view.n_slices));
+  k_loss<<<(unsigned)n_blocks, 32 * warps, 0, ctx->stream>>>(mk->view, a);
+  DHJ_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  const bool want_all = fd && out_f_all;
+  DHJ_CUDA(ctx, ctx->h_res.reserve(res_bytes * (want_all ? 2 : 1)));
+  DHJ_CUDA(ctx, cudaMemcpyAsync(ctx->h_res.p, fd ? ctx->d_fg.p : ctx->d_f.p, res_bytes, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+  if (want_all)
+    DHJ_CUDA(ctx, cudaMemcpyAsync((unsigned char*)ctx->h_res.p + res_bytes, ctx->d_f.p, res_bytes,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  DHJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const double* res = (const double*)ctx->h_res.p;
+  if (want_all) memcpy(out_f_all, (const unsigned char*)ctx->h_res.p + res_bytes, res_bytes);
+  if (!fd) {
+    memcpy(out_f, res, res_bytes);
+  } else {
+    for (int64_t c = 0; c < B; ++c) {
+      out_f[c] = res[c * kFdPoints];
+      memcpy(out_g + c * kNumParams, res + c * kFdPoints + 1, kNumParams * sizeof(double));
+    }
+  }
+  return DHJ_OK;
+}
+
+int dhj_loss_batch(dhj_ctx* ctx, const dhj_market* market, const double* x, const int32_t* market_index,
+                   int64_t B, double* out_loss) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  return run_loss(ctx, market, x, market_index, B, 0, 0.0, out_loss, nullptr, nullptr);
+}
+
+int dhj_loss_fd(dhj_ctx* ctx, const dhj_market* market, const double* x, const int32_t* market_index,
+                int64_t C, double h, double* out_f, double* out_g, double* out_f_all) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  if (!(h > 0.0)) return fail(ctx, DHJ_ERR_ARG, "h must be > 0");
+  return run_loss(ctx, market, x, market_index, C, 1, h, out_f, out_g, out_f_all);
+}
+
+int dhj_market_prices(dhj_ctx* ctx, const dhj_market* mk, const double* x, const int32_t* market_index,
+                      int64_t B, double* out_prices) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  DHJ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int* d_index = nullptr;
+  int rc = stage_x(ctx, mk, x, market_index, B, &d_index);
+  if (rc) return rc;
+  if (!out_prices) return fail(ctx, DHJ_ERR_ARG, "null output");
+  if (B == 0) return DHJ_OK;
+  const size_t ob = (size_t)B * mk->M * sizeof(double);
+  DHJ_CUDA(ctx, ctx->d_prices.reserve(ob));
+  DHJ_CUDA(ctx, ctx->h_res.reserve(ob));
+  // without an index every x uses market 0: a zero table does that
+  if (!d_index) {
+    DHJ_CUDA(ctx, ctx->d_idx.reserve((size_t)B * sizeof(int)));
+    DHJ_CUDA(ctx, cudaMemsetAsync(ctx->d_idx.p, 0, (size_t)B * sizeof(int), ctx->stream));
+    d_index = (const int*)ctx->d_idx.p;
+  }
+  PriceArgs a;
+  a.params = (const double*)ctx->d_x.p; a.S0 = (const double*)mk->d_S0.p; a.s0_stride = 1;
+  a.row_index = d_index; a.P = B; a.transform = 1; a.out = (double*)ctx->d_prices.p;
+  const int blocks = price_grid_blocks(ctx, B * (long long)mk->view.n_slices);
+  k_price<<<blocks, kThreadsPerBlock, 0, ctx->stream>>>(mk->view, a);
+  DHJ_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  DHJ_CUDA(ctx, cudaMemcpyAsync(ctx->h_res.p, ctx->d_prices.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+  DHJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out_prices, ctx->h_res.p, ob);
+  return DHJ_OK;
+}
+
+// ---- the remaining public methods of DoubleHeston --------------------------------------------
+// small synchronous helper: host arrays in -> kernel -> host arrays out through the loss staging buffers
+namespace {
+struct Staged {
+  dhj_ctx* ctx;
+  size_t in_bytes = 0, out_bytes = 0;
+  int begin(size_t in_b, size_t out_b) {
+    in_bytes = BookHost::align8(in_b); out_bytes = out_b;
+    DHJ_CUDA(ctx, cudaSetDevice(ctx->device));
+    DHJ_CUDA(ctx, ctx->h_x.reserve(in_bytes));
+    DHJ_CUDA(ctx, ctx->d_x.reserve(in_bytes));
+    DHJ_CUDA(ctx, ctx->d_prices.reserve(out_bytes));
+    DHJ_CUDA(ctx, ctx->h_res.reserve(out_bytes));
+    return DHJ_OK;
+  }
+  unsigned char* hin() { return (unsigned char*)ctx->h_x.p; }
+  unsigned char* din() { return (unsigned char*)ctx->d_x.p; }
+  int upload() {
+    DHJ_CUDA(ctx, cudaMemcpyAsync(ctx->d_x.p, ctx->h_x.p, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return DHJ_OK;
+  }
+  int download() {
+    DHJ_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    DHJ_CUDA(ctx, cudaMemcpyAsync(ctx->h_res.p, ctx->d_prices.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DHJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DHJ_OK;
+  }
+};
+}  // namespace
+
+int dhj_cf(dhj_ctx* ctx, const double* params, double r, double q, double tau, const double* u, int32_t n,
+           double* out_re, double* out_im) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  if (!params || !u || !out_re || !out_im || n < 0) return fail(ctx, DHJ_ERR_ARG, "bad arguments");
+  if (n == 0) return DHJ_OK;
+  Staged st{ctx};
+  const size_t pb = kNumParams * sizeof(double), ub = (size_t)n * sizeof(double);
+  int rc = st.begin(pb + ub, 2 * ub);
+  if (rc) return rc;
+  memcpy(st.hin(), params, pb);
+  memcpy(st.hin() + pb, u, ub);
+  if ((rc = st.upload())) return rc;
+  double* dout = (double*)ctx->d_prices.p;
+  k_cf<<<(n + 127) / 128, 128, 0, ctx->stream>>>((const double*)st.din(), r, q, tau, (const double*)(st.din() + pb),
+                                                  n, dout, dout + n);
+  if ((rc = st.download())) return rc;
+  memcpy(out_re, ctx->h_res.p, ub);
+  memcpy(out_im, (unsigned char*)ctx->h_res.p + ub, ub);
+  return DHJ_OK;
+}
+
+int dhj_truncation_range(dhj_ctx* ctx, const double* params, int64_t P, const double* S0, int64_t s0_stride,
+                         double r, const double* strike, const double* maturity, int32_t M, double L,
+                         double* out_ab) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  if (!params || !S0 || !strike || !maturity || !out_ab || P < 0 || M < 0) return fail(ctx, DHJ_ERR_ARG, "bad arguments");
+  if (s0_stride != 0 && s0_stride != 1) return fail(ctx, DHJ_ERR_ARG, "s0_stride must be 0 or 1");
+  if (P == 0 || M == 0) return DHJ_OK;
+  if (P * (int64_t)M > (int64_t)1 << 28) return fail(ctx, DHJ_ERR_ARG, "P*M too large for this helper");
+  Staged st{ctx};
+  const size_t pb = (size_t)P * kNumParams * sizeof(double), sb = (s0_stride ? (size_t)P : 1) * sizeof(double);
+  const size_t mb = (size_t)M * sizeof(double);
+  int rc = st.begin(pb + sb + 2 * mb, (size_t)P * M * 2 * sizeof(double));
+  if (rc) return rc;
+  memcpy(st.hin(), params, pb);
+  memcpy(st.hin() + pb, S0, sb);
+  memcpy(st.hin() + pb + sb, strike, mb);
+  memcpy(st.hin() + pb + sb + mb, maturity, mb);
+  if ((rc = st.upload())) return rc;
+  const long long n = P * (long long)M;
+  k_truncation_range<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+      (const double*)st.din(), P, (const double*)(st.din() + pb), s0_stride, (const double*)(st.din() + pb + sb),
+      (const double*)(st.din() + pb + sb + mb), M, r, L, (double*)ctx->d_prices.p);
+  if ((rc = st.download())) return rc;
+  memcpy(out_ab, ctx->h_res.p, st.out_bytes);
+  return DHJ_OK;
+}
+
+int dhj_chi_psi(dhj_ctx* ctx, const int32_t* k, int32_t n, double c, double d, double a, double b,
+                double* out_chi, double* out_psi) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  if (!k || !out_chi || !out_psi || n < 0) return fail(ctx, DHJ_ERR_ARG, "bad arguments");
+  if (n == 0) return DHJ_OK;
+  Staged st{ctx};
+  const size_t kb = (size_t)n * sizeof(int), ob = (size_t)n * sizeof(double);
+  int rc = st.begin(kb, 2 * ob);
+  if (rc) return rc;
+  memcpy(st.hin(), k, kb);
+  if ((rc = st.upload())) return rc;
+  double* dout = (double*)ctx->d_prices.p;
+  k_chi_psi<<<(n + 127) / 128, 128, 0, ctx->stream>>>((const int*)st.din(), n, c, d, a, b, dout, dout + n);
+  if ((rc = st.download())) return rc;
+  memcpy(out_chi, ctx->h_res.p, ob);
+  memcpy(out_psi, (unsigned char*)ctx->h_res.p + ob, ob);
+  return DHJ_OK;
+}
+
+// ---- measurement -----------------------------------------------------------------------------
+int dhj_fp64_peak(dhj_ctx* ctx, int32_t iters, double* tflops, double* milliseconds) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  if (iters < 1 || !tflops) return fail(ctx, DHJ_ERR_ARG, "bad arguments");
+  DHJ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int threads = 256, blocks = ctx->sm_count * 8;
+  DHJ_CUDA(ctx, ctx->d_peak.reserve((size_t)threads * blocks * sizeof(double)));
+  cudaEvent_t e0, e1;
+  DHJ_CUDA(ctx, cudaEventCreate(&e0));
+  DHJ_CUDA(ctx, cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {           // first repetition is the warm-up
+    DHJ_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    k_fp64_peak<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->d_peak.p, iters, 0.999999, 1e-7);
+    DHJ_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    DHJ_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    DHJ_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    DHJ_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  const double flop = 2.0 * (double)threads * blocks * (double)iters * kPeakChains * kPeakUnroll;
+  *tflops = flop / ((double)best * 1e-3) / 1e12;
+  if (milliseconds) *milliseconds = best;
+  return DHJ_OK;
+}
+
+}  // extern "C"

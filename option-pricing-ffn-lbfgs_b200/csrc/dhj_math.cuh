@@ -1,0 +1,278 @@
+// dhj_math.cuh — per-thread FP64 arithmetic of the COS pricer for the Double-Heston + Merton-jump model.
+//
+// Everything here is scalar code for ONE cosine index k of ONE (parameter set, maturity) pass; the
+// warp-level organisation (k = lane + 32*i, shuffles, strike loops) lives in dhj_engine.cuh.
+// The functions restate the formulas of the reference in float64:
+//     truncation range   /root/reference/src/models/double_heston.py:100-139
+//     characteristic fn  /root/reference/src/models/double_heston.py:48-97
+//     payoff coefficients /root/reference/src/models/double_heston.py:141-158, 172-190
+// Where it is cheap the reference's own operation order is kept (so the arguments of sin/cos/exp
+// are the same doubles the reference feeds to libm); where it is expensive the algebra is
+// simplified (no g = (beta-d)/(beta+d); the three outer complex exponentials and e^{-iua} merged
+// into one exp and one cos).  DESIGN.md §4 lists every deviation and its measured effect.
+//
+// The file compiles with nvcc (device) and with g++ (tests/host_emu: a test-only emulation that
+// lets the CPU test-suite check this arithmetic against the golden fixtures without a GPU; the
+// product never runs it).  Build with FMA contraction OFF (-fmad=false / -ffp-contract=off):
+// fused operations are written explicitly with fma() where wanted.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define DHJ_HD __host__ __device__ __forceinline__
+#else
+#define DHJ_HD inline
+#endif
+
+namespace dhj {
+
+constexpr int kNumParams = 13;
+constexpr double kPi = 3.141592653589793;      // == numpy.pi
+
+// 13 model parameters in calibrator x-vector order (lbfgs_calibrator.py:53-57)
+struct Params {
+  double v0[2], kappa[2], theta[2], sigma[2], rho[2];
+  double lam, mu, sj;
+};
+
+DHJ_HD Params load_params(const double* __restrict__ p) {
+  Params m;
+  m.v0[0] = p[0]; m.kappa[0] = p[1]; m.theta[0] = p[2]; m.sigma[0] = p[3]; m.rho[0] = p[4];
+  m.v0[1] = p[5]; m.kappa[1] = p[6]; m.theta[1] = p[7]; m.sigma[1] = p[8]; m.rho[1] = p[9];
+  m.lam = p[10]; m.mu = p[11]; m.sj = p[12];
+  return m;
+}
+
+// exp/tanh transform of the calibrator (lbfgs_calibrator.py:62-87)
+DHJ_HD Params transform_params(const double* __restrict__ x) {
+  Params m;
+  m.v0[0] = exp(x[0]); m.kappa[0] = exp(x[1]); m.theta[0] = exp(x[2]); m.sigma[0] = exp(x[3]);
+  m.rho[0] = tanh(x[4]);
+  m.v0[1] = exp(x[5]); m.kappa[1] = exp(x[6]); m.theta[1] = exp(x[7]); m.sigma[1] = exp(x[8]);
+  m.rho[1] = tanh(x[9]);
+  m.lam = exp(x[10]); m.mu = x[11]; m.sj = exp(x[12]);
+  return m;
+}
+
+// 1000*(max(0, s1^2-2 k1 t1) + max(0, s2^2-2 k2 t2)); Python max(0, e) is `e if e > 0 else 0`
+// so a NaN excess contributes 0 (lbfgs_calibrator.py:111-116)
+DHJ_HD double feller_penalty(const Params& m) {
+  double e1 = m.sigma[0] * m.sigma[0] - 2.0 * m.kappa[0] * m.theta[0];
+  double e2 = m.sigma[1] * m.sigma[1] - 2.0 * m.kappa[1] * m.theta[1];
+  double p1 = (e1 > 0.0) ? e1 : 0.0;
+  double p2 = (e2 > 0.0) ? e2 : 0.0;
+  return 1000.0 * (p1 + p2);
+}
+
+// quantities that depend on the parameter set (and r, q) only
+struct SetConsts {
+  double kappa[2], kk[2];      // kappa, kappa^2
+  double rs[2];                // rho*sigma
+  double s2[2], inv_s2[2];     // sigma^2, fl(1/sigma^2)
+  double c[2];                 // kappa*theta/sigma^2
+  double v0[2];
+  double drift;                // r - q - lam*(exp(mu + sj^2/2) - 1)       double_heston.py:82-83
+  double lam, mu, hsj2;        // hsj2 = 0.5*sj^2
+};
+
+DHJ_HD SetConsts make_set_consts(const Params& m, double r, double q) {
+  SetConsts s;
+  for (int j = 0; j < 2; ++j) {
+    s.kappa[j] = m.kappa[j];
+    s.kk[j] = m.kappa[j] * m.kappa[j];
+    s.rs[j] = m.rho[j] * m.sigma[j];
+    s.s2[j] = m.sigma[j] * m.sigma[j];
+    s.inv_s2[j] = 1.0 / s.s2[j];
+    s.c[j] = m.kappa[j] * m.theta[j] / s.s2[j];
+    s.v0[j] = m.v0[j];
+  }
+  s.hsj2 = 0.5 * (m.sj * m.sj);
+  double comp = exp(m.mu + s.hsj2) - 1.0;
+  s.drift = r - q - m.lam * comp;
+  s.lam = m.lam; s.mu = m.mu;
+  return s;
+}
+
+// ---- truncation range ----------------------------------------------------------------------
+// c1, c2 of one variance factor, in the reference's operation order (double_heston.py:101-119).
+// Note r*tau enters once PER FACTOR and neither q nor the jump compensator appear: kept as is.
+DHJ_HD void factor_cumulants(double tau, double r, double v0, double lm, double vbar, double vv, double rho,
+                             double* c1, double* c2) {
+  double e = exp(-lm * tau);
+  double e2 = exp(-2.0 * lm * tau);
+  double ome = 1.0 - e;
+  *c1 = r * tau + ome * (vbar - v0) / (2.0 * lm) - vbar * tau / 2.0;
+  double lm2 = lm * lm, vv2 = vv * vv;
+  double t1 = vv * tau * lm * e * (v0 - vbar) * (8.0 * lm * rho - 4.0 * vv);
+  double t2 = lm * rho * vv * ome * (16.0 * vbar - 8.0 * v0);
+  double t3 = 2.0 * vbar * lm * tau * (-4.0 * lm * rho * vv + vv2 + 4.0 * lm2);
+  double t4 = vv2 * ((vbar - 2.0 * v0) * e2 + vbar * (6.0 * e - 7.0) + 2.0 * v0);
+  double t5 = 8.0 * lm2 * (v0 - vbar) * ome;
+  *c2 = 1.0 / (8.0 * (lm2 * lm)) * ((((t1 + t2) + t3) + t4) + t5);
+}
+
+// a0, b0 = c1 -+ L*sqrt(|c2|) before the strike-dependent widening (double_heston.py:121-132)
+DHJ_HD void truncation_range(const Params& m, double T, double r, double L, double* a0, double* b0) {
+  double c1a, c2a, c1b, c2b;
+  factor_cumulants(T, r, m.v0[0], m.kappa[0], m.theta[0], m.sigma[0], m.rho[0], &c1a, &c2a);
+  factor_cumulants(T, r, m.v0[1], m.kappa[1], m.theta[1], m.sigma[1], m.rho[1], &c1b, &c2b);
+  double c1 = c1a + c1b + m.lam * T * m.mu;
+  double c2 = c2a + c2b + m.lam * T * (m.sj * m.sj + m.mu * m.mu);
+  double h = L * sqrt(fabs(c2));
+  *a0 = c1 - h;
+  *b0 = c1 + h;
+}
+
+// Python `a = min(a, y)` / `b = max(b, y)` (double_heston.py:136-137): the second argument wins
+// only on a strict comparison, so a NaN a/b survives and a NaN y is dropped.
+DHJ_HD double py_min(double a, double y) { return (y < a) ? y : a; }
+DHJ_HD double py_max(double b, double y) { return (y > b) ? y : b; }
+
+// quantities of one COS pass = one (parameter set, maturity, [a,b]) triple
+struct PassConsts {
+  double a, b, w;     // a, b, b - a
+  double tw;          // 2/(b-a)
+  double T, lamT;     // maturity, lam*T
+  double eb, ea;      // exp(b), exp(a)
+};
+
+DHJ_HD PassConsts make_pass_consts(const SetConsts& s, double a, double b, double T) {
+  PassConsts p;
+  p.a = a; p.b = b; p.w = b - a; p.tw = 2.0 / p.w; p.T = T; p.lamT = s.lam * T;
+  p.eb = exp(b); p.ea = exp(a);
+  return p;
+}
+
+// ---- characteristic function ----------------------------------------------------------------
+// One variance factor: returns A_j and B_j*v0_j.
+//   beta = kappa - i rho sigma u ;  d = sqrt(beta^2 + sigma^2 u (u+i)) ;  E = exp(-d T)
+//   m = beta - d ; pl = beta + d ; D = pl - m E          [1 - gE = D/pl ; 1 - g = 2d/pl]
+//   B = (m/sigma^2) (1-E)/(1-gE) = (m/sigma^2) (1-E) pl / D
+//   A = (kappa theta/sigma^2) (m T - 2 log((1-gE)/(1-g))) ,  (1-gE)/(1-g) = D/(2d)
+// (double_heston.py:64-71, 85-87).  beta^2, sigma^2 u (u+i), csqrt and exp(-dT) follow the
+// reference/glibc operation order; g itself is never formed.
+struct FactorTerms { double Ar, Ai, Bvr, Bvi; };
+
+DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) {
+  const double kap = s.kappa[j];
+  const double bi = -(s.rs[j] * u);                 // Im beta
+  const double s2u = s.s2[j] * u;
+  const double zr = (s.kk[j] - bi * bi) + s2u * u;  // Re(beta^2) + Re(sigma^2 u (u+i))
+  const double kb = kap * bi;
+  const double zi = (kb + kb) + s2u;
+  // d = csqrt(z), glibc algorithm for finite z (hypot, then the branch on the sign of Re z)
+  const double h = sqrt(fma(zr, zr, zi * zi));
+  double dr, di;
+  if (zi == 0.0) {
+    if (zr < 0.0) { dr = 0.0; di = copysign(sqrt(-zr), zi); }
+    else { dr = fabs(sqrt(zr)); di = copysign(0.0, zi); }
+  } else if (zr > 0.0) {
+    dr = sqrt(0.5 * (h + zr));
+    di = 0.5 * (zi / dr);
+  } else {
+    double t = sqrt(0.5 * (h - zr));
+    dr = fabs(0.5 * (zi / t));
+    di = copysign(t, zi);
+  }
+  // E = exp(-d T)
+  const double er = exp(-dr * T);
+  double sn, cs;
+  sincos(-di * T, &sn, &cs);
+  const double Er = er * cs, Ei = er * sn;
+  const double mr = kap - dr, mi = bi - di;         // beta - d
+  const double pr = kap + dr, pi_ = bi + di;        // beta + d
+  // D = pl - m*E
+  const double Dr = pr - (mr * Er - mi * Ei);
+  const double Di = pi_ - (mr * Ei + mi * Er);
+  const double nD = fma(Dr, Dr, Di * Di);
+  const double inD = 1.0 / nD;
+  // Q = (1-E) * pl / D = (1-E) * pl * conj(D) / |D|^2
+  const double ar = 1.0 - Er, ai = -Ei;
+  const double tr = ar * pr - ai * pi_, ti = ar * pi_ + ai * pr;
+  const double Qr = (tr * Dr + ti * Di) * inD, Qi = (ti * Dr - tr * Di) * inD;
+  // B*v0 = (m * inv_s2) * Q * v0
+  const double msr = mr * s.inv_s2[j], msi = mi * s.inv_s2[j];
+  const double Br = msr * Qr - msi * Qi, Bi = msr * Qi + msi * Qr;
+  // log(D/(2d)) : modulus from |D|^2/(4|d|^2) with |d|^2 = |z| = h ; argument from D*conj(d)
+  const double lr = 0.5 * log(nD / (4.0 * h));
+  const double li = atan2(Di * dr - Dr * di, Dr * dr + Di * di);
+  FactorTerms f;
+  f.Ar = s.c[j] * (mr * T - 2.0 * lr);
+  f.Ai = s.c[j] * (mi * T - 2.0 * li);
+  f.Bvr = Br * s.v0[j];
+  f.Bvi = Bi * s.v0[j];
+  return f;
+}
+
+// everything the strike loop needs for one k (KTerm is kept in registers, KPL of them per lane)
+struct KTerm {
+  double G;      // Re(phi(u_k) e^{-i u_k a})                double_heston.py:187
+  double u;      // (k*pi)/(b-a)                              double_heston.py:166
+  double inv1;   // 1/(1+u^2)
+  double invu;   // 1/u (0 for k = 0, where psi_0 is special-cased)
+  double sb;     // sin(u (b-a))
+  double t1;     // cos(u (b-a)) * e^b
+  double t3;     // (u * sin(u (b-a))) * e^b
+};
+
+DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k) {
+  KTerm t;
+  const double u = ((double)k * kPi) / p.w;
+  t.u = u;
+  // exponent of cf_heston: ((A0 + A1) + A2) + B1 v01 + B2 v02 ; A0 = i*(drift*u)*T
+  const FactorTerms f1 = heston_factor(s, 0, u, p.T);
+  const FactorTerms f2 = heston_factor(s, 1, u, p.T);
+  double xr = ((f1.Ar + f2.Ar) + f1.Bvr) + f2.Bvr;
+  double xi = ((((s.drift * u) * p.T + f1.Ai) + f2.Ai) + f1.Bvi) + f2.Bvi;
+  // jump: lamT * (exp(i u mu - hsj2 u^2) - 1)                 double_heston.py:93
+  const double ej = exp(-(s.hsj2 * (u * u)));
+  double sj, cj;
+  sincos(u * s.mu, &sj, &cj);
+  xr += p.lamT * (ej * cj - 1.0);
+  xi += p.lamT * (ej * sj);
+  // Re( cf_heston * cf_jump * e^{-i u a} ) with the three exponentials merged
+  t.G = exp(xr) * cos(xi - u * p.a);
+  double sbv, cbv;
+  sincos(u * p.w, &sbv, &cbv);
+  t.sb = sbv;
+  t.t1 = cbv * p.eb;
+  t.t3 = (u * sbv) * p.eb;
+  t.inv1 = 1.0 / (1.0 + u * u);
+  t.invu = (k == 0) ? 0.0 : 1.0 / u;
+  return t;
+}
+
+// strike-dependent constants of one option
+struct StrikeConsts {
+  double K, x, ex;     // strike, log(K/S0), exp(x)
+};
+
+DHJ_HD StrikeConsts make_strike_consts(double K, double S0) {
+  StrikeConsts c;
+  c.K = K; c.x = log(K / S0); c.ex = exp(c.x);
+  return c;
+}
+
+// w_k * Re(phi_k e^{-i u_k a}) * V_k for one (k, strike)        double_heston.py:141-158, 176-188
+//   call: (c,d) = (x, b) ; put: (c,d) = (a, x)
+DHJ_HD double payoff_term(const KTerm& t, const PassConsts& p, const StrikeConsts& sc, double S0,
+                          bool is_call, int k) {
+  const double xa = sc.x - p.a;
+  double sn, cs;
+  sincos(t.u * xa, &sn, &cs);
+  double chi, psi, V;
+  if (is_call) {
+    chi = t.inv1 * (((t.t1 - cs * sc.ex) + t.t3) - (t.u * sn) * sc.ex);
+    psi = (k == 0) ? (p.b - sc.x) : t.invu * (t.sb - sn);
+    V = p.tw * (S0 * chi - sc.K * psi);
+  } else {
+    chi = t.inv1 * ((cs * sc.ex - p.ea) + (t.u * sn) * sc.ex);
+    psi = (k == 0) ? xa : t.invu * sn;
+    V = p.tw * (sc.K * psi - S0 * chi);
+  }
+  double term = t.G * V;
+  return (k == 0) ? 0.5 * term : term;
+}
+
+}  // namespace dhj

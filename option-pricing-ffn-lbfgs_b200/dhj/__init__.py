@@ -1,0 +1,14 @@
+"""dhj — host-side Python over libdhj.so: B200 COS pricing of the Double-Heston + Merton-jump model.
+
+    from dhj import default_context
+    ctx = default_context()
+    prices = ctx.price_grid(params, S0, strikes, maturities, r)      # float64[P, nT, nK]
+
+The drop-in replacements for the reference's modules live beside this package under `src/`
+(src/models/double_heston.py, src/calibration/lbfgs_calibrator.py, src/data/synthetic_generator.py).
+"""
+from ._native import (Context, Market, NativeError, default_context, load_library, EXPORTS, LIB_PATH,
+                      N_PARAMS, FD_POINTS)
+
+__all__ = ["Context", "Market", "NativeError", "default_context", "load_library", "EXPORTS", "LIB_PATH",
+           "N_PARAMS", "FD_POINTS"]

@@ -1,0 +1,223 @@
+"""GPU parity tests proper: every call goes through the C-ABI of libdhj.so (ctypes) and is compared with
+the golden fixtures produced by the unmodified reference, and with the NumPy oracle on seeded samples.
+
+Tolerances (north-star): 1e-10 relative price error, 1e-9 absolute loss error per evaluation.
+Where a price is itself rounding noise of a badly conditioned sum (deep OTM short-dated, T = 30y: SURVEY
+H4) the error is judged against the conditioning scale max(S0, K) * e^b instead, as the reference's own
+NumPy-vectorised restatement has to be (tests/test_oracle_golden.py).
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from oracle import cos_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PRICE_RTOL = 1e-10
+LOSS_ATOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import dhj
+    c = dhj.Context(0)
+    yield c
+    c.close()
+
+
+def test_known_answers(ctx, golden):
+    g = golden("known_answers.npz")
+    got = ctx.price_grid(g["params"], 100.0, g["strikes"], g["maturities"], 0.05)[0]
+    assert rel_err(got, g["prices"]).max() <= PRICE_RTOL
+    demo = ctx.price_list(g["demo_params"], 100.0, [100.0, 100.0], [1.0, 1.0], [1, 0], 0.05)[0]
+    assert rel_err(demo, [g["demo_call"], g["demo_put"]]).max() <= PRICE_RTOL
+    # put-call parity, the one check the reference's demo performs (double_heston.py:292-299)
+    assert abs((demo[0] - demo[1]) - (100 - 100 * np.exp(-0.05))) < 0.01
+
+
+def test_grid15_golden(ctx, golden):
+    g = golden("prices_grid15.npz")
+    got = ctx.price_grid(g["params"], g["spots"], g["k_rel"], g["maturities"], float(g["r"]), scale_by_spot=True)
+    err = rel_err(got, g["prices"])
+    print("grid15: max rel err %.3e median %.3e" % (err.max(), np.median(err)))
+    assert err.max() <= PRICE_RTOL
+    # same through the list entry point with per-set strikes, in a scrambled option order
+    K = np.tile(g["k_rel"][None, :] * g["spots"][:, None] / 100.0, (1, 3))
+    T = np.repeat(g["maturities"], 5)
+    perm = np.random.default_rng(1).permutation(15)
+    got2 = ctx.price_list(g["params"], g["spots"], K[:, perm], T[perm], np.ones(15), float(g["r"]))
+    assert rel_err(got2, g["prices"].reshape(150, 15)[:, perm]).max() <= PRICE_RTOL
+
+
+def test_truncation_range_golden(ctx, golden):
+    g = golden("prices_grid15.npz")
+    K = (g["k_rel"] * 100.0 / 100.0)
+    sel = np.where(g["spots"] == 100.0)[0]
+    ab = ctx.truncation_range(g["params"][sel], 100.0, np.tile(K, 3), np.repeat(g["maturities"], 5), float(g["r"]))
+    want = g["ab"][sel].reshape(len(sel), 15, 2)
+    assert np.abs(ab - want).max() <= 1e-13
+
+
+@pytest.mark.parametrize("tag", ["main", "edge"])
+def test_dense_surface_golden(ctx, golden, tag):
+    g = golden("dense_surface.npz")
+    Ks, Ts = g[f"{tag}_strikes"], g[f"{tag}_maturities"]
+    got = ctx.price_grid(g["params"], 100.0, Ks, Ts, float(g["r"]), N=256)
+    want = g[f"{tag}_prices"]
+    abs_err = np.abs(got - want) / 100.0
+    print(tag, "abs/S0 max %.3e" % abs_err.max())
+    assert abs_err.max() <= 2e-13
+    big = want > 0.5
+    assert rel_err(got[big], want[big]).max() <= PRICE_RTOL
+    if tag == "edge":
+        # the widening must actually bind somewhere in this fixture, else the slow path is untested
+        ab = g["edge_ab"]
+        assert (np.abs(ab[:, :, 0, 0] - ab[:, :, -1, 0]) > 0).any() or (np.abs(ab[:, :, 0, 1] - ab[:, :, -1, 1]) > 0).any()
+
+
+def test_edge_cases_golden(ctx, golden):
+    g = golden("edge_cases.npz")
+    worst = 0.0
+    for i in range(g["prices"].shape[0]):
+        S0, K, T, r, q, call, N = g["meta"][i]
+        want = g["prices"][i]
+        got = ctx.price_list(g["params"][i], S0, [K], [T], [call], r, q, int(N))[0, 0]
+        if np.isnan(want):
+            assert np.isnan(got), (i, got)
+            continue
+        sigma1 = g["params"][i][3]
+        if sigma1 <= 1e-3:
+            # vol-of-vol -> 0: the reference's beta-d cancels catastrophically (its own value moves by
+            # 3e-4 between sigma=1e-6 and 1e-3); only a loose agreement is meaningful
+            assert abs(got - want) <= 1e-3 * want
+            continue
+        a, b = g["ab"][i]
+        scale = max(S0, K) * max(1.0, np.exp(b))            # magnitude of the summands
+        err = abs(got - want)
+        assert err <= PRICE_RTOL * abs(want) or err <= 4e-14 * scale, (i, got, want, err / scale)
+        worst = max(worst, err / scale)
+    print("edge cases: worst abs err / conditioning scale = %.3e" % worst)
+
+
+def test_cf_golden(ctx, golden):
+    g = golden("cf_values.npz")
+    for p in range(g["cf"].shape[0]):
+        for i, tau in enumerate(g["taus"]):
+            got = ctx.cf(g["params"][p], float(g["r"]), float(g["q"]), float(tau), g["us"])
+            want = g["cf"][p, i]
+            # the exponent X of phi = exp(X) carries ~1e-15*|X| absolute error, |X| up to ~150 here
+            assert (np.abs(got - want) <= 2e-13 * np.abs(want) + 1e-300).all(), (p, i)
+
+
+def test_chi_psi(ctx):
+    # double_heston.py:141-158 against the scalar oracle
+    a, b, x = -2.8282625135277004, 2.9482625135277005, np.log(95.0 / 100.0)
+    ks = np.array([0, 1, 2, 17, 64, 127, 255])
+    chi, psi = ctx.chi_psi(ks, x, b, a, b)
+    for j, k in enumerate(ks):
+        c_ref, p_ref = O._chi_psi_scalar(int(k), x, b, a, b)
+        assert abs(chi[j] - c_ref) <= 1e-13 * max(1.0, abs(c_ref))
+        assert abs(psi[j] - p_ref) <= 1e-13 * max(1.0, abs(p_ref))
+
+
+def test_random_sample_vs_oracle(ctx):
+    """2 000 seeded parameter sets x the 15-option grid against the vectorised oracle (C2 sub-sample)."""
+    rng = np.random.default_rng(20260101)
+    P = 2000
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(P, 13))
+    got = ctx.price_grid(params, 100.0, O.GENERATOR_STRIKES_REL, O.GENERATOR_MATURITIES, 0.03)
+    K = np.tile(O.GENERATOR_STRIKES_REL, 3); T = np.repeat(O.GENERATOR_MATURITIES, 5)
+    want = O.price_batch(params, 100.0, K, T, np.ones(15), 0.03).reshape(P, 3, 5)
+    err = rel_err(got, want)
+    print("C2 sub-sample: max rel err %.3e median %.3e" % (err.max(), np.median(err)))
+    assert err.max() <= PRICE_RTOL
+
+
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 100, 129, 300, 512])
+def test_ragged_n(ctx, N):
+    rng = np.random.default_rng(N)
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(7, 13))
+    K = np.array([80.0, 100.0, 125.0]); T = np.array([0.5, 0.5, 1.5]); c = np.array([1, 0, 1])
+    got = ctx.price_list(params, 100.0, K, T, c, 0.02, 0.01, N)
+    want = O.price_batch(params, 100.0, K, T, c, 0.02, 0.01, N)
+    assert (np.abs(got - want) <= 1e-10 * np.abs(want) + 1e-11).all()
+
+
+def test_empty_and_errors(ctx):
+    import dhj
+    assert ctx.price_list(np.zeros((0, 13)), 100.0, [100.0], [1.0], [1], 0.05).shape == (0, 1)
+    assert ctx.price_list(np.ones((2, 13)), 100.0, [], [], [], 0.05).shape == (2, 0)
+    with pytest.raises(dhj.NativeError):
+        ctx.price_list(np.ones((1, 13)), 100.0, [100.0], [1.0], [1], 0.05, N=0)
+    # NaN parameters give NaN prices, not an error (the reference returns NaN silently)
+    p = np.full((1, 13), np.nan)
+    assert np.isnan(ctx.price_list(p, 100.0, [100.0], [1.0], [1], 0.05)).all()
+
+
+@pytest.mark.parametrize("tag", ["c1", "ragged"])
+def test_loss_golden(ctx, golden, tag):
+    g = golden("loss_cases.npz")
+    mk = ctx.market(float(g[f"{tag}_spot"]), float(g[f"{tag}_r"]), g[f"{tag}_strike"], g[f"{tag}_maturity"],
+                    g[f"{tag}_is_call"], g[f"{tag}_market"])
+    got = mk.loss_batch(g[f"{tag}_x"])
+    want = g[f"{tag}_loss"]
+    assert np.array_equal(got == 1e10, want == 1e10)
+    err = np.abs(got - want)
+    print(tag, "loss: max abs err %.3e (rel to loss %.3e)" % (err.max(), (err / np.abs(want)).max()))
+    assert (err <= LOSS_ATOL * np.maximum(1.0, np.abs(want))).all()
+    # one-launch FD: f, the 14 stencil losses and scipy's gradient rule
+    n_fd = g[f"{tag}_fd_f"].shape[0]
+    f, grad, f_all = mk.loss_fd(g[f"{tag}_x"][:n_fd], 1e-8, want_all=True)
+    assert np.abs(f_all - g[f"{tag}_fd_f"]).max() <= LOSS_ATOL
+    assert np.array_equal(f, f_all[:, 0])
+    for c in range(n_fd):
+        x = g[f"{tag}_x"][c]
+        dx = (x + 1e-8) - x
+        assert np.array_equal(grad[c], (f_all[c, 1:] - f_all[c, 0]) / dx)          # the rule itself, exactly
+        noise = (1e-13 * abs(f[c]) + 1e-15) / 1e-8                                  # SURVEY H1 noise floor
+        assert np.abs(grad[c] - g[f"{tag}_fd_g"][c]).max() <= 10 * noise
+    # model prices at x (calibrate's re-pricing)
+    pr = mk.prices(g[f"{tag}_x"][:3])
+    want_pr = O.price_batch(O.transform_params(g[f"{tag}_x"][:3]), float(g[f"{tag}_spot"]), g[f"{tag}_strike"],
+                            g[f"{tag}_maturity"], g[f"{tag}_is_call"], float(g[f"{tag}_r"]))
+    assert rel_err(pr, want_pr).max() <= PRICE_RTOL
+    mk.close()
+
+
+def test_trajectory_replay(ctx, golden):
+    """Every x the REFERENCE optimiser visited (3 starts, 3 206 evaluations): GPU loss within 1e-9 abs."""
+    g = golden("calib_trajectory.npz")
+    mk = ctx.market(float(g["spot"]), float(g["r"]), g["strike"], g["maturity"], g["is_call"], g["market"])
+    worst = 0.0
+    for s in range(3):
+        xs, fs = g[f"s{s}_xs"], g[f"s{s}_fs"]
+        got = mk.loss_batch(xs)
+        assert np.array_equal(got == 1e10, fs == 1e10)
+        err = np.abs(got - fs) / np.maximum(1.0, np.abs(fs))
+        worst = max(worst, err.max())
+    print("trajectory replay: worst abs loss error %.3e over 3206 reference evaluations" % worst)
+    assert worst <= LOSS_ATOL
+    mk.close()
+
+
+def test_many_markets(ctx):
+    """Per-calibration markets (C5 shape): market_index routes each x to its own spot/strikes/prices."""
+    rng = np.random.default_rng(5)
+    n = 6
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(n, 13))
+    spots = rng.uniform(90, 110, size=n)
+    K = np.tile(O.GENERATOR_STRIKES_REL[None, :] * spots[:, None] / 100.0, (1, 3))
+    T = np.repeat(O.GENERATOR_MATURITIES, 5)
+    market = O.price_batch(params, spots, K, T, np.ones(15), 0.03) * (1 + 0.02 * rng.standard_normal((n, 15)))
+    mk = ctx.market(spots, 0.03, K, T, np.ones(15), market)
+    x = O.inverse_transform_params(params) + 0.05 * rng.standard_normal((n, 13))
+    idx = np.array([3, 0, 5, 1, 4, 2])
+    got = mk.loss_batch(x, idx)
+    for i in range(n):
+        j = idx[i]
+        want = O.loss_batch(x[i], spots[j], 0.03, K[j], T, np.ones(15), market[j])[0]
+        assert abs(got[i] - want) <= LOSS_ATOL
+    f, grad = mk.loss_fd(x, 1e-8, idx)
+    assert np.abs(f - got).max() == 0.0
+    mk.close()
