@@ -231,7 +231,7 @@ class DoubleHestonJumpCalibrator:
     @staticmethod
     def _minimize(fun_and_grad, x0, maxiter):
         return minimize(fun=fun_and_grad, x0=x0, jac=True, method='L-BFGS-B',
-                        options={'maxiter': maxiter, 'ftol': 1e-9, 'gtol': 1e-6, 'disp': False})
+                        options={'maxiter': maxiter, 'ftol': 1e-9, 'gtol': 1e-6})
 
     def calibrate(self, maxiter: int = 300, multi_start: int = 3) -> CalibrationResult:
         """Calibrate to the market prices with `multi_start` L-BFGS-B runs; the best (lowest loss) wins."""

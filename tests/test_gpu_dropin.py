@@ -1,0 +1,149 @@
+"""GPU tests of the drop-in modules (the reference's Python API on top of libdhj.so)."""
+import os
+import pickle
+import sys
+import time
+
+import numpy as np
+import pytest
+
+from conftest import PKG, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    for sub in ("models", "calibration", "data"):
+        p = os.path.join(PKG, "src", sub)
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import double_heston
+    import lbfgs_calibrator
+    import synthetic_generator
+    return double_heston, lbfgs_calibrator, synthetic_generator
+
+
+TS = dict(v01=0.04, kappa1=2.0, theta1=0.04, sigma1=0.3, rho1=-0.5, v02=0.04, kappa2=1.5, theta2=0.04, sigma2=0.2,
+          rho2=-0.3, lambda_j=0.1, mu_j=0.0, sigma_j=0.1)
+
+
+def test_double_heston_object(mods, golden):
+    dh, _, _ = mods
+    g = golden("known_answers.npz")
+    for i, T in enumerate(g["maturities"]):
+        for j, K in enumerate(g["strikes"]):
+            price = dh.DoubleHeston(S0=100.0, K=float(K), T=float(T), r=0.05, option_type='call', **TS).pricing(N=128)
+            assert isinstance(price, np.float64)
+            assert rel_err(price, g["prices"][i, j]) <= 1e-10
+    m = dh.DoubleHeston(100.0, 100.0, 1.0, 0.05, option_type='C', **TS)
+    a, b = m.truncationRange()
+    assert abs(a - g["ab"][2, 0]) <= 1e-14 and abs(b - g["ab"][2, 1]) <= 1e-14
+    assert m.characteristic_function(0.0, 1.0) == 1.0
+    assert np.iscomplexobj(m.characteristic_function(np.array([0.5, 1.0]), 1.0))
+    assert m.psi_k(0, -0.1, b, a, b) == b + 0.1
+    # first-letter rule (double_heston.py:172): every non-'C' string is a put
+    call = [dh.DoubleHeston(100.0, 100.0, 1.0, 0.05, option_type=t, **TS).pricing() for t in ('call', 'C', 'c', 'Call')]
+    put = [dh.DoubleHeston(100.0, 100.0, 1.0, 0.05, option_type=t, **TS).pricing() for t in ('put', 'P', 'x', 'european call')]
+    assert len(set(call)) == 1 and len(set(put)) == 1
+    assert rel_err(call[0], 13.545233402249403) <= 1e-10 and rel_err(put[0], 8.66817585183412) <= 1e-10
+    assert rel_err(dh.DoubleHeston(100.0, 100.0, 1.0, 0.05, q=0.02, **TS).pricing(), 12.293326084471488) <= 1e-10
+
+
+def test_reference_sanity_checks(mods):
+    """The range/monotonicity checks of the reference's own suite (tests/test_suite.py:203-262)."""
+    dh, _, _ = mods
+    price = lambda K, T: dh.DoubleHeston(S0=100.0, K=K, T=T, r=0.05, option_type='call', **TS).pricing(N=128)
+    assert 2.0 < price(100.0, 1.0) < 15.0
+    ks = [price(K, 1.0) for K in (90, 95, 100, 105, 110)]
+    assert np.sum(np.diff(ks) < 0) >= 3
+    assert np.all(np.diff([price(100, T) for T in (0.25, 0.5, 1.0)]) > 0)
+    assert all(np.isfinite(price(K, T)) for K, T in ((100, 0.25), (100, 2.0), (80, 1.0), (120, 1.0)))
+
+
+def c1_calibrator(cal, g):
+    opts = [{"strike": float(k), "maturity": float(t), "price": float(p), "option_type": "call"}
+            for k, t, p in zip(g["strike"], g["maturity"], g["market"])]
+    return cal.DoubleHestonJumpCalibrator(float(g["spot"]), float(g["r"]), opts)
+
+
+def test_compute_loss_and_counters(mods, golden):
+    _, cal, _ = mods
+    g = golden("initial_guess.npz")
+    c = c1_calibrator(cal, g)
+    f0 = c.compute_loss(g["g0"])
+    assert abs(f0 - float(g["f_g0"])) <= 1e-9 and c.n_calls == 1 and c.best_loss == f0
+    f1 = c.compute_loss(g["g1"])
+    assert abs(f1 - float(g["f_g1"])) <= 1e-9 and c.n_calls == 2 and c.best_loss == f0
+    x = g["g0"].copy(); x[1] = 800.0
+    assert c.compute_loss(x) == 1e10 and c.best_loss == f0          # sentinel does not touch best_loss
+    f, grad = c.compute_loss_and_grad(g["g0"])
+    assert f == f0 and grad.shape == (13,) and c.n_calls == 17
+
+
+def test_calibrate_c1(mods, golden):
+    """README configuration: 15 options, N=128, 13 parameters, multi_start=3, maxiter=300, np.random.seed(0)."""
+    _, cal, _ = mods
+    g = golden("calib_trajectory.npz")
+    gi = golden("initial_guess.npz")
+    c = c1_calibrator(cal, gi)
+    c.calibrate(maxiter=2, multi_start=1)                            # warm-up (module import, first launches)
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    res = c.calibrate(maxiter=300, multi_start=3)
+    wall = time.perf_counter() - t0
+    ref_best = min(float(g[f"s{s}_fun"]) for s in range(3))
+    print(f"calibrate(300,3): {wall:.3f} s wall, final_loss {res.final_loss:.6e} (reference best-of-3 {ref_best:.6e}), "
+          f"nit {res.iterations}, '{res.message}'")
+    assert isinstance(res, cal.CalibrationResult)
+    assert wall < 1.0                                                # north-star: under 1 s
+    assert res.final_loss * 100 < 1.0                                # the reference suite's own criterion (test 4.1)
+    assert res.final_loss <= 10 * ref_best + 1e-7                    # as good as the reference's optimum (chaotic: H1)
+    assert set(res.parameters) == set(c.param_names) and res.model_prices.shape == (15,)
+    assert np.abs(res.model_prices - res.market_prices).max() / res.market_prices.max() < 0.01
+    assert res.calibration_time <= wall and res.success in (True, False)
+    # same starting points as the reference's run (global RNG order preserved)
+    np.random.seed(0)
+    assert np.array_equal(c.get_initial_guess(0), g["s0_x0"]) and np.array_equal(c.get_initial_guess(1), g["s1_x0"])
+
+
+def test_lockstep_equals_sequential(mods, golden):
+    _, cal, _ = mods
+    gi = golden("initial_guess.npz")
+    out = []
+    for batched in (True, False):
+        c = c1_calibrator(cal, gi)
+        c.batch_starts = batched
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        r = c.calibrate(maxiter=40, multi_start=3)
+        out.append((r.final_loss, r.iterations, tuple(r.parameters.values()), c.n_calls, c.best_loss))
+        print("batched" if batched else "sequential", f"{time.perf_counter() - t0:.3f} s", r.final_loss, r.iterations)
+    assert out[0] == out[1]                                          # batching starts does not change any trajectory
+
+
+def test_generator_seed42(mods, golden, tmp_path, capsys):
+    _, cal, gen = mods
+    g = golden("generator_seed42.npz")
+    np.random.seed(42)
+    path = str(tmp_path / "synth.pkl")
+    res = gen.generate_synthetic_calibrations(20, path)
+    capsys.readouterr()
+    assert len(res) == 20 and all(isinstance(r, cal.CalibrationResult) for r in res)
+    model = np.array([r.model_prices for r in res])
+    market = np.array([r.market_prices for r in res])
+    assert rel_err(model, g["model_prices"]).max() <= 1e-10
+    assert rel_err(market, g["market_prices"]).max() <= 1e-10
+    assert np.array_equal(np.array([r.spot for r in res]), g["spots"])
+    assert np.array_equal(np.array([[r.parameters[n] for n in c] for r, c in zip(res, [list(res[0].parameters)] * 20)]),
+                          g["params"])
+    assert [r.date for r in res] == list(g["dates"])
+    assert np.abs(np.array([r.final_loss for r in res]) - g["losses"]).max() <= 1e-12
+    assert res[0].calibration_time is None and res[0].iterations is None
+    assert res[0].message == str(g["messages"][0])
+    o = res[3].market_options[7]
+    assert o["option_type"] == "call" and o["maturity"] == 0.5 and o["strike"] == g["strikes"][3, 7]
+    with open(path, "rb") as f:
+        again = pickle.load(f)
+    assert len(again) == 20 and again[5].spot == res[5].spot
+    assert gen.generate_synthetic_calibrations(0, path) == []
