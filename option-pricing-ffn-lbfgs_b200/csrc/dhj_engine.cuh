@@ -56,7 +56,9 @@ struct WarpSmem {
   PassConsts pass;
 };
 
-__device__ __forceinline__ void stage_kblock(WarpSmem& ws, int k_base, int n_cos, int lane) {
+// not inlined: called from the regular pass and from the binding-strike pass, and the CF it contains is
+// by far the largest piece of code in the kernel (one copy keeps the hot loop inside the I-cache)
+__device__ __noinline__ void stage_kblock(WarpSmem& ws, int k_base, int n_cos, int lane) {
 #pragma unroll 1
   for (int i = 0; i < kKPerLane; ++i) {
     const int k = k_base + 32 * i + lane;
@@ -131,7 +133,7 @@ __device__ __forceinline__ void price_slice(WarpSmem& ws, const Params& m, const
 
   double a0, b0;
   truncation_range(m, T, v.r, v.L, &a0, &b0);
-  const double disc = exp(-v.r * T);
+  const double disc = fm::exp_(-v.r * T);
   __syncwarp();
   if (lane == 0) ws.set = make_set_consts(m, v.r, v.q);
   __syncwarp();

@@ -1,0 +1,241 @@
+// dhj_fastmath.cuh — branch-free FP64 elementary functions for the COS kernels.
+//
+// Why not libdevice: ncu on the first kernel (profiles/README.md, r01 v1) showed 1.7 non-FP64
+// instructions per FP64 instruction — 64-bit polynomial constants rebuilt with UMOV pairs, integer
+// range-reduction and slow-path branches (Payne-Hanek, denormal division/sqrt fix-ups) that this path
+// never needs — and an 8 300-instruction body that thrashes the instruction cache.  The arguments on
+// this path are bounded (|angle| < 2^20, exponents in [-745, 709], ratios of normal numbers), so the
+// functions below are straight-line code: FMA polynomials with coefficients in __constant__ memory
+// (operands come straight from the constant bank), magic-number rounding, integer exponent tricks.
+//
+// Accuracy (scripts/check_fastmath.py, against mpmath): sincos <= 1.5 ulp for |x| <= 1e5, exp <= 1 ulp,
+// log_ratio abs error <= 2e-16 * max(1, |log|), atan2 <= 2 ulp, rcp/div/sqrt/rsqrt <= 1 ulp.
+// NaN propagates; +-inf and out-of-range arguments give the IEEE limits where the path can produce
+// them (exp), otherwise NaN.
+//
+// Compiles with nvcc (device only) and with g++ (tests/host_emu, tests/fastmath check): on the host the
+// MUFU seeds are replaced by exact 1/x, 1/sqrt(x) rounded to 20 bits so the Newton steps are exercised.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define DHJ_FM __device__ __forceinline__
+#define DHJ_CONSTANT __constant__
+#else
+#define DHJ_FM inline
+#define DHJ_CONSTANT static const
+#endif
+
+namespace dhj {
+namespace fm {
+
+// ---- bit access --------------------------------------------------------------------------------
+DHJ_FM int lo32(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2loint(x);
+#else
+  uint64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)b;
+#endif
+}
+DHJ_FM int hi32(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x);
+#else
+  uint64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)(b >> 32);
+#endif
+}
+DHJ_FM double from_hilo(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(hi, lo);
+#else
+  uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x;
+#endif
+}
+// x with its sign bit xor-ed with bit 31 of `signmask`
+DHJ_FM double xor_sign(double x, int signmask) { return from_hilo(hi32(x) ^ (signmask & (int)0x80000000), lo32(x)); }
+
+// ---- reciprocal, division, square roots ----------------------------------------------------------
+// 20-bit seeds: MUFU.RCP64H / MUFU.RSQ64H on the device
+DHJ_FM double rcp_seed(double x) {
+#if defined(__CUDA_ARCH__)
+  double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r;
+#else
+  return from_hilo(hi32(1.0 / x), 0);
+#endif
+}
+DHJ_FM double rsqrt_seed(double x) {
+#if defined(__CUDA_ARCH__)
+  double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r;
+#else
+  return from_hilo(hi32(1.0 / sqrt(x)), 0);
+#endif
+}
+
+// 1/x for normal x (two Newton steps from the seed; <= 1 ulp)
+DHJ_FM double rcp(double x) {
+  double r = rcp_seed(x);
+  double e = fma(-x, r, 1.0);
+  r = fma(fma(e, e, e), r, r);          // r (1 + e + e^2): cubic step, 20 -> 60 bits
+  e = fma(-x, r, 1.0);
+  return fma(e, r, r);
+}
+
+// a/b for normal operands and quotient (<= 1 ulp, nearly always correctly rounded)
+DHJ_FM double div(double a, double b) {
+  const double r = rcp(b);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+
+// 1/sqrt(x) and sqrt(x) for normal x > 0 (sqrt(0) = 0 handled; <= 1 ulp)
+DHJ_FM double rsqrt(double x) {
+  double y = rsqrt_seed(x);
+  const double hx = 0.5 * x;
+  double t = fma(-(hx * y), y, 0.5);
+  y = fma(y, t, y);
+  t = fma(-(hx * y), y, 0.5);
+  return fma(y, t, y);
+}
+DHJ_FM void sqrt_rsqrt(double x, double* s_out, double* y_out) {
+  const double y = rsqrt(x);
+  double s = x * y;
+  s = fma(fma(-s, s, x), 0.5 * y, s);
+  *s_out = (x == 0.0) ? 0.0 : s;
+  *y_out = y;
+}
+DHJ_FM double sqrt_(double x) { double s, y; sqrt_rsqrt(x, &s, &y); return s; }
+
+// ---- sincos ----------------------------------------------------------------------------------------
+DHJ_CONSTANT double kSin[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                               2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+DHJ_CONSTANT double kCos[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                               -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+constexpr double kTwoOverPi = 6.36619772367581382433e-01;
+constexpr double kPio2Hi = 1.57079632679489655800e+00;
+constexpr double kPio2Mid = 6.12323399573676603587e-17;
+constexpr double kRoundMagic = 6755399441055744.0;     // 1.5 * 2^52: (x + magic) - magic = rint(x), low word = int
+
+// sin and cos of x, |x| <= ~1e5 (Cody-Waite with FMA; no Payne-Hanek path)
+DHJ_FM void sincos_(double x, double* s_out, double* c_out) {
+  const double t = fma(x, kTwoOverPi, kRoundMagic);
+  const int q = lo32(t);
+  const double n = t - kRoundMagic;
+  double r = fma(-n, kPio2Hi, x);
+  r = fma(-n, kPio2Mid, r);               // |n| < 2^17: the next term of pi/2 (1.5e-33 n) is far below 1 ulp
+  const double z = r * r;
+  double ps = kSin[5];
+  ps = fma(ps, z, kSin[4]); ps = fma(ps, z, kSin[3]); ps = fma(ps, z, kSin[2]); ps = fma(ps, z, kSin[1]);
+  ps = fma(ps, z, kSin[0]);
+  const double s = fma(r * z, ps, r);
+  double pc = kCos[5];
+  pc = fma(pc, z, kCos[4]); pc = fma(pc, z, kCos[3]); pc = fma(pc, z, kCos[2]); pc = fma(pc, z, kCos[1]);
+  pc = fma(pc, z, kCos[0]);
+  const double c = fma(z, fma(z, pc, -0.5), 1.0);
+  // quadrant: q odd swaps; bit 1 of q negates sin, bit 1 of (q+1) negates cos
+  const bool swap = (q & 1) != 0;
+  const double ss = swap ? c : s;
+  const double cc = swap ? s : c;
+  *s_out = xor_sign(ss, q << 30);
+  *c_out = xor_sign(cc, (q + 1) << 30);
+}
+DHJ_FM double cos_(double x) { double s, c; sincos_(x, &s, &c); return c; }
+
+// ---- exp -----------------------------------------------------------------------------------------
+// exp(r) = 1 + r + r^2 q(r) on |r| <= ln2/2, q minimax of degree 9 (scripts/gen_poly.py: 1.0e-16)
+DHJ_CONSTANT double kExpQ[10] = {0.50000000000000010212, 0.16666666666666674523, 0.041666666666624157875,
+                                 0.0083333333333222152106, 0.001388888891719838631, 0.00019841269886566398025,
+                                 0.00002480152132015615238, 2.7557242364849317814e-6, 2.7620076799169896683e-7,
+                                 2.5110039179932520501e-8};
+constexpr double kLog2e = 1.44269504088896338700e+00;
+constexpr double kLn2Hi = 6.93147180369123816490e-01;    // fdlibm split: hi has 32 significant bits
+constexpr double kLn2Lo = 1.90821492927058770002e-10;
+
+DHJ_FM double exp_(double x) {
+  const double t = fma(x, kLog2e, kRoundMagic);
+  const int n = lo32(t);
+  const double nf = t - kRoundMagic;
+  double r = fma(-nf, kLn2Hi, x);
+  r = fma(-nf, kLn2Lo, r);
+  double q = kExpQ[9];
+  q = fma(q, r, kExpQ[8]); q = fma(q, r, kExpQ[7]); q = fma(q, r, kExpQ[6]); q = fma(q, r, kExpQ[5]);
+  q = fma(q, r, kExpQ[4]); q = fma(q, r, kExpQ[3]); q = fma(q, r, kExpQ[2]); q = fma(q, r, kExpQ[1]);
+  q = fma(q, r, kExpQ[0]);
+  const double p = 1.0 + fma(r * r, q, r);
+  // 2^n in two factors so that results down to the smallest normal and up to DBL_MAX are exact scalings
+  const int n1 = n >> 1, n2 = n - n1;
+  double res = (p * from_hilo((n1 + 1023) << 20, 0)) * from_hilo((n2 + 1023) << 20, 0);
+  res = (x < -745.2) ? 0.0 : res;
+  res = (x > 709.79) ? (double)INFINITY : res;
+  return res;
+}
+
+// ---- log of a ratio --------------------------------------------------------------------------------
+// log(a/b) for normal a, b > 0:  a/b = 2^k * m, m in [sqrt(1/2), sqrt(2));  s = (a - b')/(a + b') with
+// b' = b * 2^k;  log m = 2 atanh(s) = 2s + s R(s^2)   (fdlibm's Lg1..Lg7, error 2^-58.45)
+DHJ_CONSTANT double kLg[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                              2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                              1.479819860511658591e-01};
+constexpr double kLn2HiFull = 6.93147180559945286227e-01;   // ln2 rounded to double
+constexpr double kLn2LoFull = 2.31904681384629955842e-17;   // ln2 - kLn2HiFull
+constexpr double kSqrt2 = 1.41421356237309514547e+00;
+constexpr double kSqrtHalf = 7.07106781186547572737e-01;
+
+DHJ_FM double log_ratio(double a, double b) {
+  // align exponents: b' = b * 2^(ea - eb) has the exponent of a, so a/b' in (1/2, 2)
+  int k = ((hi32(a) >> 20) & 0x7ff) - ((hi32(b) >> 20) & 0x7ff);
+  double bs = from_hilo(hi32(b) + (k << 20), lo32(b));
+  const bool up = a > kSqrt2 * bs, down = a < kSqrtHalf * bs;
+  bs = up ? 2.0 * bs : (down ? 0.5 * bs : bs);
+  k += up ? 1 : (down ? -1 : 0);
+  const double s = div(a - bs, a + bs);
+  const double z = s * s;
+  double R = kLg[6];
+  R = fma(R, z, kLg[5]); R = fma(R, z, kLg[4]); R = fma(R, z, kLg[3]); R = fma(R, z, kLg[2]); R = fma(R, z, kLg[1]);
+  R = fma(R, z, kLg[0]);
+  R = R * z;
+  const double kf = (double)k;
+  // k ln2 + 2s + s R, low-order parts first
+  const double res = fma(kf, kLn2HiFull, fma(s, R, fma(kf, kLn2LoFull, s + s)));
+  const double nan_probe = a + b;          // the exponent surgery above would launder a NaN b
+  return (nan_probe != nan_probe) ? nan_probe : res;
+}
+DHJ_FM double log_(double x) { return log_ratio(x, 1.0); }
+
+// ---- atan2 -----------------------------------------------------------------------------------------
+// atan(t) = t - t z P(z), z = t^2, |t| <= tan(pi/8)  (fdlibm aT[0..10], designed for |t| < 7/16)
+DHJ_CONSTANT double kAt[11] = {3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01,
+                               -1.11111104054623557880e-01, 9.09088713343650656196e-02, -7.69187620504482999495e-02,
+                               6.66107313738753120669e-02, -5.83357013379057348645e-02, 4.97687799461593236017e-02,
+                               -3.65315727442169155270e-02, 1.62858201153657823623e-02};
+constexpr double kTanPi8 = 4.14213562373095048802e-01;
+constexpr double kPiO4 = 7.85398163397448278999e-01;
+constexpr double kPiO4Lo = 3.06161699786838301793e-17;
+constexpr double kPiO2 = 1.57079632679489655800e+00;
+constexpr double kPiD = 3.14159265358979311600e+00;
+
+DHJ_FM double atan2_(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  // octant reduction without a second division: atan(mn/mx) = pi/4 + atan((mn-mx)/(mn+mx)) when mn/mx > tan(pi/8)
+  const bool hi = mn > kTanPi8 * mx;
+  const double num = hi ? mn - mx : mn;
+  const double den = hi ? mn + mx : mx;
+  const double t = div(num, den);
+  const double z = t * t;
+  double p = kAt[10];
+  p = fma(p, z, kAt[9]); p = fma(p, z, kAt[8]); p = fma(p, z, kAt[7]); p = fma(p, z, kAt[6]); p = fma(p, z, kAt[5]);
+  p = fma(p, z, kAt[4]); p = fma(p, z, kAt[3]); p = fma(p, z, kAt[2]); p = fma(p, z, kAt[1]); p = fma(p, z, kAt[0]);
+  double r = fma(-(t * z), p, t);
+  r = hi ? (r + kPiO4Lo) + kPiO4 : r;     // atan(mn/mx) in [0, pi/4]
+  r = (ay > ax) ? kPiO2 - r : r;          // first quadrant angle
+  r = (x < 0.0) ? kPiD - r : r;
+  r = (mx == 0.0) ? ((x < 0.0 || (x == 0.0 && signbit(x))) ? kPiD : 0.0) : r;   // atan2(+-0, +-0)
+  const double nan_probe = ax + ay;       // fmax/fmin drop a NaN operand: put it back
+  r = (nan_probe != nan_probe) ? nan_probe : r;
+  return copysign(r, y);
+}
+
+}  // namespace fm
+}  // namespace dhj

@@ -25,7 +25,7 @@ struct PriceArgs {
   double* out;               // [P][M]
 };
 
-__global__ void __launch_bounds__(kThreadsPerBlock) k_price(SliceView v, PriceArgs a) {
+__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_price(SliceView v, PriceArgs a) {
   __shared__ WarpSmem ws_all[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WarpSmem& ws = ws_all[warp];
@@ -57,7 +57,7 @@ struct LossArgs {
   unsigned int* counters;    // fd: [C], zero on entry, zero on exit
 };
 
-__global__ void __launch_bounds__(kThreadsPerBlock) k_loss(SliceView v, LossArgs a) {
+__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_loss(SliceView v, LossArgs a) {
   __shared__ WarpSmem ws_all[kWarpsPerBlock];
   __shared__ double red_sq[kWarpsPerBlock];
   __shared__ int red_bad[kWarpsPerBlock];
@@ -135,18 +135,11 @@ __global__ void k_cf(const double* __restrict__ params, double r, double q, doub
   const Params m = load_params(params);
   const SetConsts s = make_set_consts(m, r, q);
   const double u = u_in[i];
-  const FactorTerms f1 = heston_factor(s, 0, u, tau), f2 = heston_factor(s, 1, u, tau);
-  double xr = ((f1.Ar + f2.Ar) + f1.Bvr) + f2.Bvr;
-  double xi = ((((s.drift * u) * tau + f1.Ai) + f2.Ai) + f1.Bvi) + f2.Bvi;
-  const double ej = exp(-(s.hsj2 * (u * u)));
-  double sj, cj;
-  sincos(u * s.mu, &sj, &cj);
-  const double lamT = s.lam * tau;
-  xr += lamT * (ej * cj - 1.0);
-  xi += lamT * (ej * sj);
+  double xr, xi;
+  cf_exponent(s, u, tau, s.lam * tau, &xr, &xi);
   double sn, cs;
-  sincos(xi, &sn, &cs);
-  const double mag = exp(xr);
+  fm::sincos_(xi, &sn, &cs);
+  const double mag = fm::exp_(xr);
   out_re[i] = mag * cs;
   out_im[i] = mag * sn;
 }
@@ -163,7 +156,7 @@ __global__ void k_truncation_range(const double* __restrict__ params, long long 
   const Params m = load_params(params + kNumParams * p);
   double a0, b0;
   truncation_range(m, maturity[o], r, L, &a0, &b0);
-  const double x = log(strike[o] / S0[p * s0_stride]);
+  const double x = fm::log_ratio(strike[o], S0[p * s0_stride]);
   out_ab[2 * i] = py_min(a0, x - 0.1);
   out_ab[2 * i + 1] = py_max(b0, x + 0.1);
 }
@@ -174,14 +167,14 @@ __global__ void k_chi_psi(const int* __restrict__ k_in, int n, double c, double 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int k = k_in[i];
-  if (k == 0) { chi[i] = exp(d) - exp(c); psi[i] = d - c; return; }
-  const double u = ((double)k * kPi) / (b - a);
+  const double ed = fm::exp_(d), ec = fm::exp_(c);
+  if (k == 0) { chi[i] = ed - ec; psi[i] = d - c; return; }
+  const double u = fm::div((double)k * kPi, b - a);
   double sd, cd, sc, cc;
-  sincos(u * (d - a), &sd, &cd);
-  sincos(u * (c - a), &sc, &cc);
-  const double ed = exp(d), ec = exp(c);
-  chi[i] = (1.0 / (1.0 + u * u)) * (((cd * ed - cc * ec) + (u * sd) * ed) - (u * sc) * ec);
-  psi[i] = (1.0 / u) * (sd - sc);
+  fm::sincos_(u * (d - a), &sd, &cd);
+  fm::sincos_(u * (c - a), &sc, &cc);
+  chi[i] = fm::rcp(1.0 + u * u) * (((cd * ed - cc * ec) + (u * sd) * ed) - (u * sc) * ec);
+  psi[i] = fm::rcp(u) * (sd - sc);
 }
 
 // 8 independent FMA chains per thread; 2 flop per FMA

@@ -14,13 +14,16 @@
 // The file compiles with nvcc (device) and with g++ (tests/host_emu: a test-only emulation that
 // lets the CPU test-suite check this arithmetic against the golden fixtures without a GPU; the
 // product never runs it).  Build with FMA contraction OFF (-fmad=false / -ffp-contract=off):
-// fused operations are written explicitly with fma() where wanted.
+// fused operations are written explicitly with fma() where wanted.  Elementary functions come from
+// dhj_fastmath.cuh (branch-free, <= 1-2 ulp), not from libdevice.
 #pragma once
 #include <math.h>
 #include <stdint.h>
 
+#include "dhj_fastmath.cuh"
+
 #if defined(__CUDACC__)
-#define DHJ_HD __host__ __device__ __forceinline__
+#define DHJ_HD __device__ __forceinline__
 #else
 #define DHJ_HD inline
 #endif
@@ -47,11 +50,16 @@ DHJ_HD Params load_params(const double* __restrict__ p) {
 // exp/tanh transform of the calibrator (lbfgs_calibrator.py:62-87)
 DHJ_HD Params transform_params(const double* __restrict__ x) {
   Params m;
-  m.v0[0] = exp(x[0]); m.kappa[0] = exp(x[1]); m.theta[0] = exp(x[2]); m.sigma[0] = exp(x[3]);
+  // exp for the ten positive parameters in one rolled loop (one copy of the code), tanh from libm
+  // (two calls per loss evaluation; accuracy near 0 matters more than speed here)
+  double e[kNumParams];
+#pragma unroll 1
+  for (int i = 0; i < kNumParams; ++i) e[i] = fm::exp_(x[i]);
+  m.v0[0] = e[0]; m.kappa[0] = e[1]; m.theta[0] = e[2]; m.sigma[0] = e[3];
   m.rho[0] = tanh(x[4]);
-  m.v0[1] = exp(x[5]); m.kappa[1] = exp(x[6]); m.theta[1] = exp(x[7]); m.sigma[1] = exp(x[8]);
+  m.v0[1] = e[5]; m.kappa[1] = e[6]; m.theta[1] = e[7]; m.sigma[1] = e[8];
   m.rho[1] = tanh(x[9]);
-  m.lam = exp(x[10]); m.mu = x[11]; m.sj = exp(x[12]);
+  m.lam = e[10]; m.mu = x[11]; m.sj = e[12];
   return m;
 }
 
@@ -83,12 +91,12 @@ DHJ_HD SetConsts make_set_consts(const Params& m, double r, double q) {
     s.kk[j] = m.kappa[j] * m.kappa[j];
     s.rs[j] = m.rho[j] * m.sigma[j];
     s.s2[j] = m.sigma[j] * m.sigma[j];
-    s.inv_s2[j] = 1.0 / s.s2[j];
-    s.c[j] = m.kappa[j] * m.theta[j] / s.s2[j];
+    s.inv_s2[j] = fm::rcp(s.s2[j]);
+    s.c[j] = fm::div(m.kappa[j] * m.theta[j], s.s2[j]);
     s.v0[j] = m.v0[j];
   }
   s.hsj2 = 0.5 * (m.sj * m.sj);
-  double comp = exp(m.mu + s.hsj2) - 1.0;
+  double comp = fm::exp_(m.mu + s.hsj2) - 1.0;
   s.drift = r - q - m.lam * comp;
   s.lam = m.lam; s.mu = m.mu;
   return s;
@@ -99,27 +107,31 @@ DHJ_HD SetConsts make_set_consts(const Params& m, double r, double q) {
 // Note r*tau enters once PER FACTOR and neither q nor the jump compensator appear: kept as is.
 DHJ_HD void factor_cumulants(double tau, double r, double v0, double lm, double vbar, double vv, double rho,
                              double* c1, double* c2) {
-  double e = exp(-lm * tau);
-  double e2 = exp(-2.0 * lm * tau);
+  double e = fm::exp_(-lm * tau);
+  double e2 = fm::exp_(-2.0 * lm * tau);
   double ome = 1.0 - e;
-  *c1 = r * tau + ome * (vbar - v0) / (2.0 * lm) - vbar * tau / 2.0;
+  *c1 = r * tau + fm::div(ome * (vbar - v0), 2.0 * lm) - vbar * tau / 2.0;
   double lm2 = lm * lm, vv2 = vv * vv;
   double t1 = vv * tau * lm * e * (v0 - vbar) * (8.0 * lm * rho - 4.0 * vv);
   double t2 = lm * rho * vv * ome * (16.0 * vbar - 8.0 * v0);
   double t3 = 2.0 * vbar * lm * tau * (-4.0 * lm * rho * vv + vv2 + 4.0 * lm2);
   double t4 = vv2 * ((vbar - 2.0 * v0) * e2 + vbar * (6.0 * e - 7.0) + 2.0 * v0);
   double t5 = 8.0 * lm2 * (v0 - vbar) * ome;
-  *c2 = 1.0 / (8.0 * (lm2 * lm)) * ((((t1 + t2) + t3) + t4) + t5);
+  *c2 = fm::rcp(8.0 * (lm2 * lm)) * ((((t1 + t2) + t3) + t4) + t5);
 }
 
 // a0, b0 = c1 -+ L*sqrt(|c2|) before the strike-dependent widening (double_heston.py:121-132)
 DHJ_HD void truncation_range(const Params& m, double T, double r, double L, double* a0, double* b0) {
-  double c1a, c2a, c1b, c2b;
-  factor_cumulants(T, r, m.v0[0], m.kappa[0], m.theta[0], m.sigma[0], m.rho[0], &c1a, &c2a);
-  factor_cumulants(T, r, m.v0[1], m.kappa[1], m.theta[1], m.sigma[1], m.rho[1], &c1b, &c2b);
-  double c1 = c1a + c1b + m.lam * T * m.mu;
-  double c2 = c2a + c2b + m.lam * T * (m.sj * m.sj + m.mu * m.mu);
-  double h = L * sqrt(fabs(c2));
+  double c1 = 0.0, c2 = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < 2; ++j) {                 // rolled: one copy of the cumulant code
+    double c1j, c2j;
+    factor_cumulants(T, r, m.v0[j], m.kappa[j], m.theta[j], m.sigma[j], m.rho[j], &c1j, &c2j);
+    c1 += c1j; c2 += c2j;
+  }
+  c1 = c1 + m.lam * T * m.mu;
+  c2 = c2 + m.lam * T * (m.sj * m.sj + m.mu * m.mu);
+  double h = L * fm::sqrt_(fabs(c2));
   *a0 = c1 - h;
   *b0 = c1 + h;
 }
@@ -132,6 +144,7 @@ DHJ_HD double py_max(double b, double y) { return (y > b) ? y : b; }
 // quantities of one COS pass = one (parameter set, maturity, [a,b]) triple
 struct PassConsts {
   double a, b, w;     // a, b, b - a
+  double rw;          // 1/(b-a) (seed for the correctly rounded u_k = (k pi)/(b-a))
   double tw;          // 2/(b-a)
   double T, lamT;     // maturity, lam*T
   double eb, ea;      // exp(b), exp(a)
@@ -139,8 +152,8 @@ struct PassConsts {
 
 DHJ_HD PassConsts make_pass_consts(const SetConsts& s, double a, double b, double T) {
   PassConsts p;
-  p.a = a; p.b = b; p.w = b - a; p.tw = 2.0 / p.w; p.T = T; p.lamT = s.lam * T;
-  p.eb = exp(b); p.ea = exp(a);
+  p.a = a; p.b = b; p.w = b - a; p.rw = fm::rcp(p.w); p.tw = fm::div(2.0, p.w); p.T = T; p.lamT = s.lam * T;
+  p.eb = fm::exp_(b); p.ea = fm::exp_(a);
   return p;
 }
 
@@ -150,7 +163,7 @@ DHJ_HD PassConsts make_pass_consts(const SetConsts& s, double a, double b, doubl
 //   m = beta - d ; pl = beta + d ; D = pl - m E          [1 - gE = D/pl ; 1 - g = 2d/pl]
 //   B = (m/sigma^2) (1-E)/(1-gE) = (m/sigma^2) (1-E) pl / D
 //   A = (kappa theta/sigma^2) (m T - 2 log((1-gE)/(1-g))) ,  (1-gE)/(1-g) = D/(2d)
-// (double_heston.py:64-71, 85-87).  beta^2, sigma^2 u (u+i), csqrt and exp(-dT) follow the
+// (double_heston.py:64-71, 85-87).  beta^2, sigma^2 u (u+i) and the csqrt formula follow the
 // reference/glibc operation order; g itself is never formed.
 struct FactorTerms { double Ar, Ai, Bvr, Bvi; };
 
@@ -161,24 +174,20 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) 
   const double zr = (s.kk[j] - bi * bi) + s2u * u;  // Re(beta^2) + Re(sigma^2 u (u+i))
   const double kb = kap * bi;
   const double zi = (kb + kb) + s2u;
-  // d = csqrt(z), glibc algorithm for finite z (hypot, then the branch on the sign of Re z)
-  const double h = sqrt(fma(zr, zr, zi * zi));
-  double dr, di;
-  if (zi == 0.0) {
-    if (zr < 0.0) { dr = 0.0; di = copysign(sqrt(-zr), zi); }
-    else { dr = fabs(sqrt(zr)); di = copysign(0.0, zi); }
-  } else if (zr > 0.0) {
-    dr = sqrt(0.5 * (h + zr));
-    di = 0.5 * (zi / dr);
-  } else {
-    double t = sqrt(0.5 * (h - zr));
-    dr = fabs(0.5 * (zi / t));
-    di = copysign(t, zi);
-  }
+  // d = csqrt(z) as glibc does it: h = |z|, t = sqrt((h + |zr|)/2), other = zi/(2t); the roles of t and
+  // `other` swap when Re z < 0.  (Re z >= kappa^2 > 0 for |rho| <= 1; the other case is kept for safety.)
+  double h, yh;
+  fm::sqrt_rsqrt(fma(zr, zr, zi * zi), &h, &yh);
+  double t, yt;
+  fm::sqrt_rsqrt(0.5 * (h + fabs(zr)), &t, &yt);
+  const double other = (0.5 * zi) * yt;
+  const bool pos = zr >= 0.0;
+  const double dr = pos ? t : fabs(other);
+  const double di = pos ? other : copysign(t, zi);
   // E = exp(-d T)
-  const double er = exp(-dr * T);
+  const double er = fm::exp_(-dr * T);
   double sn, cs;
-  sincos(-di * T, &sn, &cs);
+  fm::sincos_(-di * T, &sn, &cs);
   const double Er = er * cs, Ei = er * sn;
   const double mr = kap - dr, mi = bi - di;         // beta - d
   const double pr = kap + dr, pi_ = bi + di;        // beta + d
@@ -186,7 +195,7 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) 
   const double Dr = pr - (mr * Er - mi * Ei);
   const double Di = pi_ - (mr * Ei + mi * Er);
   const double nD = fma(Dr, Dr, Di * Di);
-  const double inD = 1.0 / nD;
+  const double inD = fm::rcp(nD);
   // Q = (1-E) * pl / D = (1-E) * pl * conj(D) / |D|^2
   const double ar = 1.0 - Er, ai = -Ei;
   const double tr = ar * pr - ai * pi_, ti = ar * pi_ + ai * pr;
@@ -195,8 +204,8 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) 
   const double msr = mr * s.inv_s2[j], msi = mi * s.inv_s2[j];
   const double Br = msr * Qr - msi * Qi, Bi = msr * Qi + msi * Qr;
   // log(D/(2d)) : modulus from |D|^2/(4|d|^2) with |d|^2 = |z| = h ; argument from D*conj(d)
-  const double lr = 0.5 * log(nD / (4.0 * h));
-  const double li = atan2(Di * dr - Dr * di, Dr * dr + Di * di);
+  const double lr = 0.5 * fm::log_ratio(nD, 4.0 * h);
+  const double li = fm::atan2_(Di * dr - Dr * di, Dr * dr + Di * di);
   FactorTerms f;
   f.Ar = s.c[j] * (mr * T - 2.0 * lr);
   f.Ai = s.c[j] * (mi * T - 2.0 * li);
@@ -205,7 +214,29 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) 
   return f;
 }
 
-// everything the strike loop needs for one k (KTerm is kept in registers, KPL of them per lane)
+// exponent X of cf_heston * cf_jump = exp(X) at frequency u  (double_heston.py:82-96):
+//   X = ((A0 + A1) + A2) + B1 v01 + B2 v02  +  lamT (exp(i u mu - hsj2 u^2) - 1),  A0 = i (drift u) T
+// The two factors run through ONE rolled copy of heston_factor (instruction-cache footprint).
+DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, double* xr_out, double* xi_out) {
+  double aR = 0.0, aI = (s.drift * u) * T;
+  double b1r = 0.0, b1i = 0.0, b2r = 0.0, b2i = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < 2; ++j) {
+    const FactorTerms f = heston_factor(s, j, u, T);
+    aR += f.Ar; aI += f.Ai;
+    if (j == 0) { b1r = f.Bvr; b1i = f.Bvi; } else { b2r = f.Bvr; b2i = f.Bvi; }
+  }
+  double xr = (aR + b1r) + b2r;
+  double xi = (aI + b1i) + b2i;
+  const double ej = fm::exp_(-(s.hsj2 * (u * u)));
+  double sj, cj;
+  fm::sincos_(u * s.mu, &sj, &cj);
+  xr += lamT * (ej * cj - 1.0);
+  xi += lamT * (ej * sj);
+  *xr_out = xr; *xi_out = xi;
+}
+
+// everything the strike loop needs for one k
 struct KTerm {
   double G;      // Re(phi(u_k) e^{-i u_k a})                double_heston.py:187
   double u;      // (k*pi)/(b-a)                              double_heston.py:166
@@ -218,28 +249,22 @@ struct KTerm {
 
 DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k) {
   KTerm t;
-  const double u = ((double)k * kPi) / p.w;
+  // u = (k*pi)/(b-a): quotient from the precomputed reciprocal plus one correction step
+  const double kpi = (double)k * kPi;
+  const double q0 = kpi * p.rw;
+  const double u = fma(fma(-p.w, q0, kpi), p.rw, q0);
   t.u = u;
-  // exponent of cf_heston: ((A0 + A1) + A2) + B1 v01 + B2 v02 ; A0 = i*(drift*u)*T
-  const FactorTerms f1 = heston_factor(s, 0, u, p.T);
-  const FactorTerms f2 = heston_factor(s, 1, u, p.T);
-  double xr = ((f1.Ar + f2.Ar) + f1.Bvr) + f2.Bvr;
-  double xi = ((((s.drift * u) * p.T + f1.Ai) + f2.Ai) + f1.Bvi) + f2.Bvi;
-  // jump: lamT * (exp(i u mu - hsj2 u^2) - 1)                 double_heston.py:93
-  const double ej = exp(-(s.hsj2 * (u * u)));
-  double sj, cj;
-  sincos(u * s.mu, &sj, &cj);
-  xr += p.lamT * (ej * cj - 1.0);
-  xi += p.lamT * (ej * sj);
+  double xr, xi;
+  cf_exponent(s, u, p.T, p.lamT, &xr, &xi);
   // Re( cf_heston * cf_jump * e^{-i u a} ) with the three exponentials merged
-  t.G = exp(xr) * cos(xi - u * p.a);
+  t.G = fm::exp_(xr) * fm::cos_(xi - u * p.a);
   double sbv, cbv;
-  sincos(u * p.w, &sbv, &cbv);
+  fm::sincos_(u * p.w, &sbv, &cbv);
   t.sb = sbv;
   t.t1 = cbv * p.eb;
   t.t3 = (u * sbv) * p.eb;
-  t.inv1 = 1.0 / (1.0 + u * u);
-  t.invu = (k == 0) ? 0.0 : 1.0 / u;
+  t.inv1 = fm::rcp(1.0 + u * u);
+  t.invu = (k == 0) ? 0.0 : fm::rcp(u);
   return t;
 }
 
@@ -250,28 +275,28 @@ struct StrikeConsts {
 
 DHJ_HD StrikeConsts make_strike_consts(double K, double S0) {
   StrikeConsts c;
-  c.K = K; c.x = log(K / S0); c.ex = exp(c.x);
+  c.K = K; c.x = fm::log_ratio(K, S0); c.ex = fm::exp_(c.x);
   return c;
 }
 
 // w_k * Re(phi_k e^{-i u_k a}) * V_k for one (k, strike)        double_heston.py:141-158, 176-188
-//   call: (c,d) = (x, b) ; put: (c,d) = (a, x)
+//   call: (c,d) = (x, b) ; put: (c,d) = (a, x).  One code path: the two payoffs differ by selects.
 DHJ_HD double payoff_term(const KTerm& t, const PassConsts& p, const StrikeConsts& sc, double S0,
                           bool is_call, int k) {
   const double xa = sc.x - p.a;
   double sn, cs;
-  sincos(t.u * xa, &sn, &cs);
-  double chi, psi, V;
-  if (is_call) {
-    chi = t.inv1 * (((t.t1 - cs * sc.ex) + t.t3) - (t.u * sn) * sc.ex);
-    psi = (k == 0) ? (p.b - sc.x) : t.invu * (t.sb - sn);
-    V = p.tw * (S0 * chi - sc.K * psi);
-  } else {
-    chi = t.inv1 * ((cs * sc.ex - p.ea) + (t.u * sn) * sc.ex);
-    psi = (k == 0) ? xa : t.invu * sn;
-    V = p.tw * (sc.K * psi - S0 * chi);
-  }
-  double term = t.G * V;
+  fm::sincos_(t.u * xa, &sn, &cs);
+  const double cex = cs * sc.ex, usex = (t.u * sn) * sc.ex;
+  // call: ((t1 - cex) + t3) - usex ; put: (cex - e^a) + usex
+  const double chi_call = ((t.t1 - cex) + t.t3) - usex;
+  const double chi_put = (cex - p.ea) + usex;
+  const double chi = t.inv1 * (is_call ? chi_call : chi_put);
+  const double psi0 = is_call ? (p.b - sc.x) : xa;                 // k = 0: d - c
+  const double psik = t.invu * (is_call ? (t.sb - sn) : sn);
+  const double psi = (k == 0) ? psi0 : psik;
+  const double spot_leg = S0 * chi, strike_leg = sc.K * psi;
+  const double V = p.tw * (is_call ? (spot_leg - strike_leg) : (strike_leg - spot_leg));
+  const double term = t.G * V;
   return (k == 0) ? 0.5 * term : term;
 }
 

@@ -30,7 +30,7 @@ static double price_one(const Params& m, double S0, double K, double T, double r
   }
   for (int off = 16; off >= 1; off >>= 1)
     for (int lane = 0; lane < 32; ++lane) lane_sum[lane] += lane_sum[lane ^ off] * ((lane & off) ? 0.0 : 1.0);
-  return exp(-r * T) * lane_sum[0];
+  return fm::exp_(-r * T) * lane_sum[0];
 }
 
 extern "C" {
@@ -70,14 +70,8 @@ void emu_cf(const double* params, double r, double q, double tau, const double* 
   for (int i = 0; i < n; ++i) {
     // w chosen so that u_k = (k*pi)/w reproduces us[i] for k = 1 is not exact; evaluate the factors directly
     double u = us[i];
-    FactorTerms f1 = heston_factor(s, 0, u, tau), f2 = heston_factor(s, 1, u, tau);
-    double xr = ((f1.Ar + f2.Ar) + f1.Bvr) + f2.Bvr;
-    double xi = ((((s.drift * u) * tau + f1.Ai) + f2.Ai) + f1.Bvi) + f2.Bvi;
-    double ej = exp(-(s.hsj2 * (u * u))), sj, cj;
-    sincos(u * s.mu, &sj, &cj);
-    double lamT = s.lam * tau;
-    xr += lamT * (ej * cj - 1.0);
-    xi += lamT * (ej * sj);
+    double xr, xi;
+    cf_exponent(s, u, tau, s.lam * tau, &xr, &xi);
     re[i] = exp(xr) * cos(xi);
     im[i] = exp(xr) * sin(xi);
   }
