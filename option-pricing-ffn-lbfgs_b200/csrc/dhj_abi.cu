@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -51,7 +52,7 @@ struct PinBuf {
 
 // Host description of the option slices (options grouped by maturity, first-appearance order).
 struct BookHost {
-  int M = 0, n_slices = 0;
+  int M = 0, n_slices = 0, max_slice = 0;
   std::vector<double> slice_T;
   std::vector<int> slice_off, pos;
   std::vector<unsigned char> call;
@@ -70,7 +71,8 @@ struct BookHost {
     n_slices = (int)slice_T.size();
     slice_off.assign(n_slices + 1, 0);
     for (int o = 0; o < m; ++o) slice_off[slice_of[o] + 1]++;
-    for (int s = 0; s < n_slices; ++s) slice_off[s + 1] += slice_off[s];
+    max_slice = 0;
+    for (int s = 0; s < n_slices; ++s) { max_slice = std::max(max_slice, slice_off[s + 1]); slice_off[s + 1] += slice_off[s]; }
     pos.assign(m, 0); call.assign(m, 0);
     std::vector<int> fill(slice_off.begin(), slice_off.end() - 1);
     for (int o = 0; o < m; ++o) {
@@ -80,7 +82,7 @@ struct BookHost {
     }
   }
   void grid(const double* maturities, int nT, int nK, int is_call_flag) {
-    M = nT * nK; n_slices = nT;
+    M = nT * nK; n_slices = nT; max_slice = nK;
     slice_T.assign(maturities, maturities + nT);
     slice_off.resize(nT + 1);
     for (int t = 0; t <= nT; ++t) slice_off[t] = t * nK;
@@ -128,6 +130,7 @@ struct dhj_ctx {
   int device = 0;
   int sm_count = 0;
   int price_blocks_per_sm = 1;
+  int batch_blocks_per_sm = 1;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   char err[512] = "";
@@ -178,10 +181,35 @@ bool is_pinned_host(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
+// k_price_batch handles slices of <= 8 strikes (one thread per k, 32 items per block batch); k_price the rest
+int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_slice, cudaStream_t st);
+
 int price_grid_blocks(const dhj_ctx* ctx, long long items) {
   long long want = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
   long long cap = (long long)ctx->sm_count * ctx->price_blocks_per_sm;
   return (int)std::max<long long>(1, std::min(want, cap));
+}
+
+int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_slice, cudaStream_t st) {
+  const long long items = a.P * (long long)v.n_slices;
+  if (max_slice <= kBatchMaxStrikes) {
+    const long long batches = (items + kBatchItems - 1) / kBatchItems;
+    const long long cap = (long long)ctx->sm_count * ctx->batch_blocks_per_sm;
+    // DHJ_DEBUG_EXTRA_SMEM (bytes): developer knob that pads the launch with unused dynamic shared memory to
+    // lower the resident block count (occupancy experiments, profiles/README.md); never set in production
+    static const size_t extra = [] {
+      const char* e = getenv("DHJ_DEBUG_EXTRA_SMEM");
+      size_t b = e ? (size_t)atol(e) : 0;
+      if (b) cudaFuncSetAttribute(k_price_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b);
+      return b;
+    }();
+    k_price_batch<<<(int)std::max<long long>(1, std::min(batches, cap)), kBatchThreads, extra, st>>>(v, a);
+  } else {
+    k_price<<<price_grid_blocks(ctx, items), kThreadsPerBlock, 0, st>>>(v, a);
+  }
+  DHJ_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  return DHJ_OK;
 }
 
 // Upload (or reuse) the packed book image + shared strike table for a pricing call on `stream`.
@@ -219,7 +247,7 @@ int check_common(dhj_ctx* ctx, const void* params, int64_t P, const void* S0, in
 }
 
 // Chunked, double-buffered host-to-host pricing: params/S0/strike rows in, price rows out.
-int run_price_host(dhj_ctx* ctx, SliceView v, const double* params, int64_t P, const double* S0,
+int run_price_host(dhj_ctx* ctx, SliceView v, int max_slice, const double* params, int64_t P, const double* S0,
                    int64_t s0_stride, const double* strike, int64_t strike_stride, double* out) {
   const int M = v.n_options;
   if (P == 0 || M == 0) return DHJ_OK;
@@ -264,10 +292,8 @@ int run_price_host(dhj_ctx* ctx, SliceView v, const double* params, int64_t P, c
     PriceArgs a;
     a.params = (const double*)din; a.S0 = (const double*)(din + pb); a.s0_stride = s0_stride ? 1 : 0;
     a.row_index = nullptr; a.P = n; a.transform = 0; a.out = (double*)sl.d_out.p;
-    const int blocks = price_grid_blocks(ctx, n * (long long)vv.n_slices);
-    k_price<<<blocks, kThreadsPerBlock, 0, sl.stream>>>(vv, a);
-    DHJ_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
+    int rc = launch_price(ctx, vv, a, max_slice, sl.stream);
+    if (rc) return rc;
     double* dst = out + lo * (int64_t)M;
     if (pin_out) {
       DHJ_CUDA(ctx, cudaMemcpyAsync(dst, sl.d_out.p, ob, cudaMemcpyDeviceToHost, sl.stream));
@@ -362,6 +388,9 @@ int dhj_init(int device, dhj_ctx** out) {
     return DHJ_ERR_CUDA;
   }
   ctx->price_blocks_per_sm = std::max(1, bps);
+  bps = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_price_batch, kBatchThreads, 0) != cudaSuccess) bps = 1;
+  ctx->batch_blocks_per_sm = std::max(1, bps);
   *out = ctx;
   return DHJ_OK;
 }
@@ -411,7 +440,7 @@ int dhj_price_list(dhj_ctx* ctx, const double* params, int64_t P, const double* 
   rc = upload_book(ctx, book, strike_stride ? nullptr : strike, strike_stride ? 0 : M, ctx->stream, &v);
   if (rc) return rc;
   v.scale_by_spot = 0; v.n_cos = N; v.r = r; v.q = q; v.L = L;
-  return run_price_host(ctx, v, params, P, S0, s0_stride, strike, strike_stride, out);
+  return run_price_host(ctx, v, book.max_slice, params, P, S0, s0_stride, strike, strike_stride, out);
 }
 
 static int grid_view(dhj_ctx* ctx, const double* strikes, int32_t nK, const double* maturities, int32_t nT,
@@ -440,7 +469,7 @@ int dhj_price_grid(dhj_ctx* ctx, const double* params, int64_t P, const double* 
   rc = grid_view(ctx, strikes, nK, maturities, nT, scale_by_spot, is_call, N, r, q, L, ctx->stream, &v);
   if (rc) return rc;
   if (P == 0) return DHJ_OK;
-  return run_price_host(ctx, v, params, P, S0, s0_stride, nullptr, 0, out);
+  return run_price_host(ctx, v, nK, params, P, S0, s0_stride, nullptr, 0, out);
 }
 
 int dhj_price_grid_dev(dhj_ctx* ctx, const double* d_params, int64_t P, const double* d_S0,
@@ -459,11 +488,7 @@ int dhj_price_grid_dev(dhj_ctx* ctx, const double* d_params, int64_t P, const do
   PriceArgs a;
   a.params = d_params; a.S0 = d_S0; a.s0_stride = s0_stride; a.row_index = nullptr; a.P = P; a.transform = 0;
   a.out = d_out;
-  const int blocks = price_grid_blocks(ctx, P * (long long)v.n_slices);
-  k_price<<<blocks, kThreadsPerBlock, 0, st>>>(v, a);
-  DHJ_CUDA(ctx, cudaGetLastError());
-  ctx->launches++;
-  return DHJ_OK;
+  return launch_price(ctx, v, a, nK, st);
 }
 
 // ---- calibration loss ------------------------------------------------------------------------
@@ -603,10 +628,8 @@ int dhj_market_prices(dhj_ctx* ctx, const dhj_market* mk, const double* x, const
   PriceArgs a;
   a.params = (const double*)ctx->d_x.p; a.S0 = (const double*)mk->d_S0.p; a.s0_stride = 1;
   a.row_index = d_index; a.P = B; a.transform = 1; a.out = (double*)ctx->d_prices.p;
-  const int blocks = price_grid_blocks(ctx, B * (long long)mk->view.n_slices);
-  k_price<<<blocks, kThreadsPerBlock, 0, ctx->stream>>>(mk->view, a);
-  DHJ_CUDA(ctx, cudaGetLastError());
-  ctx->launches++;
+  rc = launch_price(ctx, mk->view, a, mk->book.max_slice, ctx->stream);
+  if (rc) return rc;
   DHJ_CUDA(ctx, cudaMemcpyAsync(ctx->h_res.p, ctx->d_prices.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
   DHJ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   memcpy(out_prices, ctx->h_res.p, ob);

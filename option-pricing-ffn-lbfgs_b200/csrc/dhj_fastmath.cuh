@@ -152,7 +152,8 @@ constexpr double kLog2e = 1.44269504088896338700e+00;
 constexpr double kLn2Hi = 6.93147180369123816490e-01;    // fdlibm split: hi has 32 significant bits
 constexpr double kLn2Lo = 1.90821492927058770002e-10;
 
-DHJ_FM double exp_(double x) {
+// core: p * 2^n, valid for -1400 < x < 1400 (no guards)
+DHJ_FM double exp_core(double x) {
   const double t = fma(x, kLog2e, kRoundMagic);
   const int n = lo32(t);
   const double nf = t - kRoundMagic;
@@ -165,10 +166,19 @@ DHJ_FM double exp_(double x) {
   const double p = 1.0 + fma(r * r, q, r);
   // 2^n in two factors so that results down to the smallest normal and up to DBL_MAX are exact scalings
   const int n1 = n >> 1, n2 = n - n1;
-  double res = (p * from_hilo((n1 + 1023) << 20, 0)) * from_hilo((n2 + 1023) << 20, 0);
+  return (p * from_hilo((n1 + 1023) << 20, 0)) * from_hilo((n2 + 1023) << 20, 0);
+}
+// full range
+DHJ_FM double exp_(double x) {
+  double res = exp_core(x);
   res = (x < -745.2) ? 0.0 : res;
   res = (x > 709.79) ? (double)INFINITY : res;
   return res;
+}
+// for arguments known to be <= ~700 (decay factors): only the underflow side is guarded
+DHJ_FM double exp_neg(double x) {
+  const double res = exp_core(x);
+  return (x < -745.2) ? 0.0 : res;
 }
 
 // ---- log of a ratio --------------------------------------------------------------------------------
@@ -217,7 +227,8 @@ constexpr double kPiD = 3.14159265358979311600e+00;
 
 DHJ_FM double atan2_(double y, double x) {
   const double ax = fabs(x), ay = fabs(y);
-  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  const bool steep = ay > ax;                       // NaN-safe: a NaN operand lands in mn or mx and propagates
+  const double mx = steep ? ay : ax, mn = steep ? ax : ay;
   // octant reduction without a second division: atan(mn/mx) = pi/4 + atan((mn-mx)/(mn+mx)) when mn/mx > tan(pi/8)
   const bool hi = mn > kTanPi8 * mx;
   const double num = hi ? mn - mx : mn;
@@ -229,11 +240,9 @@ DHJ_FM double atan2_(double y, double x) {
   p = fma(p, z, kAt[4]); p = fma(p, z, kAt[3]); p = fma(p, z, kAt[2]); p = fma(p, z, kAt[1]); p = fma(p, z, kAt[0]);
   double r = fma(-(t * z), p, t);
   r = hi ? (r + kPiO4Lo) + kPiO4 : r;     // atan(mn/mx) in [0, pi/4]
-  r = (ay > ax) ? kPiO2 - r : r;          // first quadrant angle
+  r = steep ? kPiO2 - r : r;              // first quadrant angle
   r = (x < 0.0) ? kPiD - r : r;
   r = (mx == 0.0) ? ((x < 0.0 || (x == 0.0 && signbit(x))) ? kPiD : 0.0) : r;   // atan2(+-0, +-0)
-  const double nan_probe = ax + ay;       // fmax/fmin drop a NaN operand: put it back
-  r = (nan_probe != nan_probe) ? nan_probe : r;
   return copysign(r, y);
 }
 

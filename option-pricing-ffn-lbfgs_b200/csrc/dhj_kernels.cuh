@@ -7,6 +7,7 @@
 //   k_fp64_peak  DFMA-chain probe for the FP64 roofline denominator
 #pragma once
 #include "dhj_engine.cuh"
+#include "dhj_batch.cuh"
 
 namespace dhj {
 
@@ -42,6 +43,61 @@ __global__ void __launch_bounds__(kThreadsPerBlock, 4) k_price(SliceView v, Pric
     double* out_row = a.out + p * (long long)v.n_options;
     price_slice(ws, m, v, s, S0, strike_row, lane,
                 [&](int o, double price) { out_row[v.pos[o]] = price; });
+  }
+}
+
+// Throughput variant of k_price for slices of <= 8 strikes: see dhj_batch.cuh.
+__global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(SliceView v, PriceArgs a) {
+  __shared__ BatchSmem sm;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long n_items = a.P * (long long)v.n_slices;
+  const long long n_batches = (n_items + kBatchItems - 1) / kBatchItems;
+  for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    const long long base = batch * kBatchItems;
+    const int cnt_items = (int)min((long long)kBatchItems, n_items - base);
+    // ---- phase 1: one thread per item ----------------------------------------------------------
+    if (tid < cnt_items) {
+      const long long item = base + tid;
+      const long long p = item / v.n_slices;
+      const int s = (int)(item - p * v.n_slices);
+      const long long row = a.row_index ? (long long)a.row_index[p] : p;
+      prepare_item(sm.items[tid], v, a.params + kNumParams * p, a.transform != 0, a.S0[row * a.s0_stride],
+                   v.strike + row * v.strike_stride, s, p * (long long)v.n_options);
+    }
+    __syncthreads();
+    // ---- phase 2: one thread per cosine index ----------------------------------------------------
+#pragma unroll 1
+    for (int i = 0; i < cnt_items; ++i) {
+      const ItemRec& it = sm.items[i];
+      double* warp_partial = sm.partial[i][warp];
+      if (lane < kBatchMaxStrikes) warp_partial[lane] = 0.0;
+      __syncwarp();
+      const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
+      if (reg_mask) contract_pass(it, it.pass, reg_mask, v.n_cos, tid, warp_partial);
+      unsigned todo = it.valid_mask & it.bind_mask;          // rare: strikes with their own (a, b)
+      while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        __syncthreads();
+        if (tid == 0)
+          sm.extra_pass = make_pass_consts(it.set, py_min(it.a0, it.x[j] - 0.1), py_max(it.b0, it.x[j] + 0.1),
+                                           it.pass.T);
+        __syncthreads();
+        contract_pass(it, sm.extra_pass, 1u << j, v.n_cos, tid, warp_partial);
+      }
+    }
+    __syncthreads();
+    // ---- phase 3: add the warps' partials, discount, store -----------------------------------------
+    for (int t = tid; t < cnt_items * kBatchMaxStrikes; t += kBatchThreads) {
+      const int i = t / kBatchMaxStrikes, j = t - i * kBatchMaxStrikes;
+      const ItemRec& it = sm.items[i];
+      if (it.valid_mask & (1u << j)) {
+        const double* q = sm.partial[i][0] + j;
+        const double sum = ((q[0] + q[kBatchMaxStrikes]) + q[2 * kBatchMaxStrikes]) + q[3 * kBatchMaxStrikes];
+        a.out[it.out_row + v.pos[it.o_lo + j]] = it.disc * sum;
+      }
+    }
+    __syncthreads();
   }
 }
 

@@ -185,7 +185,7 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) 
   const double dr = pos ? t : fabs(other);
   const double di = pos ? other : copysign(t, zi);
   // E = exp(-d T)
-  const double er = fm::exp_(-dr * T);
+  const double er = fm::exp_neg(-dr * T);
   double sn, cs;
   fm::sincos_(-di * T, &sn, &cs);
   const double Er = er * cs, Ei = er * sn;
@@ -228,7 +228,7 @@ DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, dou
   }
   double xr = (aR + b1r) + b2r;
   double xi = (aI + b1i) + b2i;
-  const double ej = fm::exp_(-(s.hsj2 * (u * u)));
+  const double ej = fm::exp_neg(-(s.hsj2 * (u * u)));
   double sj, cj;
   fm::sincos_(u * s.mu, &sj, &cj);
   xr += lamT * (ej * cj - 1.0);
@@ -238,7 +238,7 @@ DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, dou
 
 // everything the strike loop needs for one k
 struct KTerm {
-  double G;      // Re(phi(u_k) e^{-i u_k a})                double_heston.py:187
+  double G;      // w_k Re(phi(u_k) e^{-i u_k a}), w_0 = 1/2     double_heston.py:187-188
   double u;      // (k*pi)/(b-a)                              double_heston.py:166
   double inv1;   // 1/(1+u^2)
   double invu;   // 1/u (0 for k = 0, where psi_0 is special-cased)
@@ -257,7 +257,8 @@ DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k) {
   double xr, xi;
   cf_exponent(s, u, p.T, p.lamT, &xr, &xi);
   // Re( cf_heston * cf_jump * e^{-i u a} ) with the three exponentials merged
-  t.G = fm::exp_(xr) * fm::cos_(xi - u * p.a);
+  // (the k = 0 weight 1/2 of double_heston.py:188 is folded in here: scaling by 2^-1 commutes exactly)
+  t.G = (fm::exp_(xr) * fm::cos_(xi - u * p.a)) * ((k == 0) ? 0.5 : 1.0);
   double sbv, cbv;
   fm::sincos_(u * p.w, &sbv, &cbv);
   t.sb = sbv;
@@ -280,24 +281,24 @@ DHJ_HD StrikeConsts make_strike_consts(double K, double S0) {
 }
 
 // w_k * Re(phi_k e^{-i u_k a}) * V_k for one (k, strike)        double_heston.py:141-158, 176-188
-//   call: (c,d) = (x, b) ; put: (c,d) = (a, x).  One code path: the two payoffs differ by selects.
+//   call: (c,d) = (x, b) ; put: (c,d) = (a, x).  `is_call` is uniform across the warp: a real branch.
 DHJ_HD double payoff_term(const KTerm& t, const PassConsts& p, const StrikeConsts& sc, double S0,
                           bool is_call, int k) {
   const double xa = sc.x - p.a;
   double sn, cs;
   fm::sincos_(t.u * xa, &sn, &cs);
   const double cex = cs * sc.ex, usex = (t.u * sn) * sc.ex;
-  // call: ((t1 - cex) + t3) - usex ; put: (cex - e^a) + usex
-  const double chi_call = ((t.t1 - cex) + t.t3) - usex;
-  const double chi_put = (cex - p.ea) + usex;
-  const double chi = t.inv1 * (is_call ? chi_call : chi_put);
-  const double psi0 = is_call ? (p.b - sc.x) : xa;                 // k = 0: d - c
-  const double psik = t.invu * (is_call ? (t.sb - sn) : sn);
-  const double psi = (k == 0) ? psi0 : psik;
-  const double spot_leg = S0 * chi, strike_leg = sc.K * psi;
-  const double V = p.tw * (is_call ? (spot_leg - strike_leg) : (strike_leg - spot_leg));
-  const double term = t.G * V;
-  return (k == 0) ? 0.5 * term : term;
+  double V;
+  if (is_call) {
+    const double chi = t.inv1 * (((t.t1 - cex) + t.t3) - usex);
+    const double psi = (k == 0) ? (p.b - sc.x) : t.invu * (t.sb - sn);
+    V = p.tw * (S0 * chi - sc.K * psi);
+  } else {
+    const double chi = t.inv1 * ((cex - p.ea) + usex);
+    const double psi = (k == 0) ? xa : t.invu * sn;
+    V = p.tw * (sc.K * psi - S0 * chi);
+  }
+  return t.G * V;
 }
 
 }  // namespace dhj
