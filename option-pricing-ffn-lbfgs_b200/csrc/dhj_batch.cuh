@@ -34,18 +34,29 @@ struct ItemRec {
   PassConsts pass;                 // regular pass: (a0, b0)
   double a0, b0, S0, disc;
   double K[kBatchMaxStrikes], x[kBatchMaxStrikes], ex[kBatchMaxStrikes];
+  double cth[kBatchMaxStrikes], sth[kBatchMaxStrikes];      // cos / sin of theta_j = u_1 (x_j - a0)
   unsigned valid_mask, bind_mask, call_mask;
   int o_lo;                        // first option (slice order) of the slice
   long long out_row;               // p * M
 };
 
+struct CoefStage { double P[32], Q[32], R[32]; };   // one warp's k-block of strike-independent coefficients
+
 struct BatchSmem {
   ItemRec items[kBatchItems];
   PassConsts extra_pass;           // pass constants of a binding strike
+  double extra_cth, extra_sth;     // and its rotation step
+  CoefStage stage[kBatchWarps];
   double partial[kBatchItems][kBatchWarps][kBatchMaxStrikes];
 };
 
 struct PriceArgs;                  // dhj_kernels.cuh
+
+// u_1 = (1*pi)/(b-a), the rotation step's frequency (same correction step as make_kterm)
+__device__ __forceinline__ double u_one(const PassConsts& p) {
+  const double q0 = kPi * p.rw;
+  return fma(fma(-p.w, q0, kPi), p.rw, q0);
+}
 
 // phase 1 for one item, executed by a single thread
 __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, const double* __restrict__ pp,
@@ -67,6 +78,7 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
     if (v.scale_by_spot) K = K * S0 / 100.0;
     const StrikeConsts sc = make_strike_consts(K, S0);
     rec.K[j] = sc.K; rec.x[j] = sc.x; rec.ex[j] = sc.ex;
+    fm::sincos_(u_one(rec.pass) * (sc.x - a0), &rec.sth[j], &rec.cth[j]);
     if (((sc.x - 0.1) < a0) || ((sc.x + 0.1) > b0)) bind |= 1u << j;
     if (v.call[o_lo + j]) call |= 1u << j;
   }
@@ -75,28 +87,47 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
   rec.o_lo = o_lo; rec.out_row = out_row;
 }
 
-// phase 2 body for one pass: this thread's k values against the strikes in `mask`; each strike's 32 lane terms
-// are added by shuffles at once and accumulated into the warp's shared-memory partial, so no accumulator
-// registers stay live across the (register-hungry) CF evaluation
-__device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConsts& pc, unsigned mask, int n_cos,
-                                              int tid, double* __restrict__ warp_partial) {
+// phase 2 body for one pass of one warp: CF at this lane's k -> strike-independent coefficients in the warp's
+// stage; four shuffle reductions (A1, A2, A3, g0); then the rotation tasks: lane = (strike j, segment s) with
+// 8-term segments, reduced over the 4 segments by two shuffles and accumulated into the warp's partial.
+__device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConsts& pc, const double* __restrict__ cth,
+                                              const double* __restrict__ sth, unsigned mask, int n_cos, int tid,
+                                              CoefStage& st, double* __restrict__ warp_partial) {
+  constexpr int kSeg = 8, kNumSeg = 32 / kSeg;
   const int lane = tid & 31;
 #pragma unroll 1
   for (int k0 = 0; k0 < n_cos; k0 += kBatchThreads) {
     const int k = k0 + tid;
-    const bool live = k < n_cos;
-    KTerm t;
-    if (live) t = make_kterm(it.set, pc, k);
-#pragma unroll 1
-    for (int j = 0; j < kBatchMaxStrikes; ++j) {
-      if (mask & (1u << j)) {
-        StrikeConsts sc;
-        sc.K = it.K[j]; sc.x = it.x[j]; sc.ex = it.ex[j];
-        const double term = live ? payoff_term(t, pc, sc, it.S0, (it.call_mask >> j) & 1u, k) : 0.0;
-        const double tot = warp_sum(term);
-        if (lane == 0) warp_partial[j] += tot;
-      }
+    KCoef c;
+    c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
+    if (k < n_cos) c = make_kcoef(make_kterm(it.set, pc, k), pc, k);
+    __syncwarp();
+    st.P[lane] = c.P; st.Q[lane] = c.Q; st.R[lane] = c.R;
+    // A1, A2 feed calls, A3 puts (uniform per pass); g0 is non-zero only in the lane that holds k = 0
+    const bool any_call = (it.call_mask & mask) != 0, any_put = (~it.call_mask & mask) != 0;
+    const double A1 = any_call ? warp_sum(c.a1) : 0.0, A2 = any_call ? warp_sum(c.a2) : 0.0;
+    const double A3 = any_put ? warp_sum(c.P) : 0.0;
+    const double g0 = __shfl_sync(kFullMask, c.g0, 0);
+    __syncwarp();
+    // task of this lane
+    const int j = lane / kNumSeg, s = lane - j * kNumSeg;
+    const bool active = (mask >> j) & 1u;
+    double val = 0.0;
+    if (active) {
+      const int kstart = (k - lane) + s * kSeg;                    // absolute k of the segment's first term
+      const double kpi = (double)kstart * kPi;
+      const double q0 = kpi * pc.rw;
+      const double u0 = fma(fma(-pc.w, q0, kpi), pc.rw, q0);
+      double sn, cs;
+      fm::sincos_(u0 * (it.x[j] - pc.a), &sn, &cs);
+      double spq, sr;
+      segment_sums(st.P + s * kSeg, st.Q + s * kSeg, st.R + s * kSeg, kSeg, cs, sn, cth[j], sth[j], &spq, &sr);
+      val = it.K[j] * sr - (it.S0 * it.ex[j]) * spq;
+      if (s == 0) val += strike_const_part((it.call_mask >> j) & 1u, it.S0, it.K[j], it.x[j], pc, A1, A2, A3, g0);
     }
+    val += __shfl_xor_sync(kFullMask, val, 1);
+    val += __shfl_xor_sync(kFullMask, val, 2);
+    if (active && s == 0) warp_partial[j] += val;
   }
 }
 

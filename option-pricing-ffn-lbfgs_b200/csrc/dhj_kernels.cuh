@@ -73,17 +73,21 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
       if (lane < kBatchMaxStrikes) warp_partial[lane] = 0.0;
       __syncwarp();
       const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
-      if (reg_mask) contract_pass(it, it.pass, reg_mask, v.n_cos, tid, warp_partial);
+      if (reg_mask) contract_pass(it, it.pass, it.cth, it.sth, reg_mask, v.n_cos, tid, sm.stage[warp], warp_partial);
       unsigned todo = it.valid_mask & it.bind_mask;          // rare: strikes with their own (a, b)
       while (todo) {
         const int j = __ffs(todo) - 1;
         todo &= todo - 1;
         __syncthreads();
-        if (tid == 0)
+        if (tid == 0) {
           sm.extra_pass = make_pass_consts(it.set, py_min(it.a0, it.x[j] - 0.1), py_max(it.b0, it.x[j] + 0.1),
                                            it.pass.T);
+          fm::sincos_(u_one(sm.extra_pass) * (it.x[j] - sm.extra_pass.a), &sm.extra_sth, &sm.extra_cth);
+        }
         __syncthreads();
-        contract_pass(it, sm.extra_pass, 1u << j, v.n_cos, tid, warp_partial);
+        // the task code indexes cth/sth by strike: point it at the single extra entry
+        contract_pass(it, sm.extra_pass, &sm.extra_cth - j, &sm.extra_sth - j, 1u << j, v.n_cos, tid, sm.stage[warp],
+                      warp_partial);
       }
     }
     __syncthreads();

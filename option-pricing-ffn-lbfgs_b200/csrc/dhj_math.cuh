@@ -32,6 +32,7 @@ namespace dhj {
 
 constexpr int kNumParams = 13;
 constexpr double kPi = 3.141592653589793;      // == numpy.pi
+constexpr double kPiLo = 1.2246467991473532e-16; // pi - kPi
 
 // 13 model parameters in calibrator x-vector order (lbfgs_calibrator.py:53-57)
 struct Params {
@@ -176,10 +177,13 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) 
   const double zi = (kb + kb) + s2u;
   // d = csqrt(z) as glibc does it: h = |z|, t = sqrt((h + |zr|)/2), other = zi/(2t); the roles of t and
   // `other` swap when Re z < 0.  (Re z >= kappa^2 > 0 for |rho| <= 1; the other case is kept for safety.)
-  double h, yh;
-  fm::sqrt_rsqrt(fma(zr, zr, zi * zi), &h, &yh);
-  double t, yt;
-  fm::sqrt_rsqrt(0.5 * (h + fabs(zr)), &t, &yt);
+  // (square roots as x * rsqrt(x): <= 1 ulp instead of correctly rounded, no zero special case; z = 0 needs
+  // kappa = 0 and u = 0, for which the reference divides by zero as well)
+  const double n2 = fma(zr, zr, zi * zi);
+  const double h = n2 * fm::rsqrt(n2);
+  const double x2 = 0.5 * (h + fabs(zr));
+  const double yt = fm::rsqrt(x2);
+  const double t = x2 * yt;
   const double other = (0.5 * zi) * yt;
   const bool pos = zr >= 0.0;
   const double dr = pos ? t : fabs(other);
@@ -259,10 +263,13 @@ DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k) {
   // Re( cf_heston * cf_jump * e^{-i u a} ) with the three exponentials merged
   // (the k = 0 weight 1/2 of double_heston.py:188 is folded in here: scaling by 2^-1 commutes exactly)
   t.G = (fm::exp_(xr) * fm::cos_(xi - u * p.a)) * ((k == 0) ? 0.5 : 1.0);
-  double sbv, cbv;
-  fm::sincos_(u * p.w, &sbv, &cbv);
+  // sin / cos of fl(u (b-a)) = k pi + delta, |delta| <~ 1e-13: sin = (-1)^k delta, cos = (-1)^k exactly in
+  // double (what libm returns for this argument), with delta from a two-term pi
+  const double kf = (double)k;
+  const double delta = fma(-kf, kPiLo, fma(-kf, kPi, u * p.w));
+  const double sbv = fm::xor_sign(delta, k << 31);
   t.sb = sbv;
-  t.t1 = cbv * p.eb;
+  t.t1 = fm::xor_sign(p.eb, k << 31);
   t.t3 = (u * sbv) * p.eb;
   t.inv1 = fm::rcp(1.0 + u * u);
   t.invu = (k == 0) ? 0.0 : fm::rcp(u);
@@ -299,6 +306,53 @@ DHJ_HD double payoff_term(const KTerm& t, const PassConsts& p, const StrikeConst
     V = p.tw * (sc.K * psi - S0 * chi);
   }
   return t.G * V;
+}
+
+// ---- rotation-based strike contraction -------------------------------------------------------------
+// With theta = pi (x - a)/(b - a) the strike enters the payoff only through cos(k theta), sin(k theta):
+//   sum_k w_k Re(phi_k e^{-i u_k a}) V_k
+//     = [call] S0 A1 - K A2 - K g0 (b - x)   or   [put] S0 e^a A3 + K g0 (x - a)
+//       + K sum_k R_k sin(k theta) - S0 e^x sum_k (P_k cos(k theta) + Q_k sin(k theta))
+// with the strike-independent  P_k = G_k tw/(1+u_k^2), Q_k = P_k u_k, R_k = G_k tw/u_k (R_0 = 0),
+// A1 = sum P_k (t1_k + t3_k), A2 = sum R_k sin(u_k (b-a)), A3 = sum P_k, g0 = G_0 tw.
+// The trigonometric sums are evaluated in segments of consecutive k: one exact sincos at the segment
+// start, then plane rotations by theta (<= 32 steps, error growth <= 32 * 1.5 ulp).  This replaces one
+// sincos per (strike, k) by ~7 FMAs.
+struct KCoef { double P, Q, R, a1, a2, g0; };
+
+DHJ_HD KCoef make_kcoef(const KTerm& t, const PassConsts& p, int k) {
+  KCoef c;
+  const double gt = t.G * p.tw;
+  c.P = gt * t.inv1;
+  c.Q = c.P * t.u;
+  c.R = gt * t.invu;                 // invu = 0 for k = 0
+  c.a1 = c.P * (t.t1 + t.t3);
+  c.a2 = c.R * t.sb;
+  c.g0 = (k == 0) ? gt : 0.0;
+  return c;
+}
+
+// sums over one segment: sum (P cos + Q sin) and sum R sin, starting from (c, s) = cos/sin(k0 theta)
+DHJ_HD void segment_sums(const double* __restrict__ P, const double* __restrict__ Q, const double* __restrict__ R,
+                         int seg, double c, double s, double cth, double sth, double* sum_pq, double* sum_r) {
+  double apq = 0.0, ar = 0.0;
+#pragma unroll 4
+  for (int i = 0; i < seg; ++i) {
+    apq = fma(P[i], c, apq);
+    apq = fma(Q[i], s, apq);
+    ar = fma(R[i], s, ar);
+    const double cn = fma(c, cth, -(s * sth));
+    s = fma(s, cth, c * sth);
+    c = cn;
+  }
+  *sum_pq = apq; *sum_r = ar;
+}
+
+// strike-dependent constant part (uses warp- or block-level sums A1, A2, A3, g0: it is linear in them)
+DHJ_HD double strike_const_part(bool is_call, double S0, double K, double x, const PassConsts& p, double A1,
+                                double A2, double A3, double g0) {
+  return is_call ? (S0 * A1 - K * A2) - (K * g0) * (p.b - x)
+                 : (S0 * p.ea) * A3 + (K * g0) * (x - p.a);
 }
 
 }  // namespace dhj

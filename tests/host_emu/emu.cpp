@@ -10,6 +10,23 @@
 
 using namespace dhj;
 
+static double butterfly_total(double* v) {        // xor-butterfly over 32 lanes, as warp_sum does
+  for (int off = 16; off >= 1; off >>= 1) {
+    double t[32];
+    for (int l = 0; l < 32; ++l) t[l] = v[l] + v[l ^ off];
+    for (int l = 0; l < 32; ++l) v[l] = t[l];
+  }
+  return v[0];
+}
+
+static double u_of(const PassConsts& p, int k) {
+  const double kpi = (double)k * kPi;
+  const double q0 = kpi * p.rw;
+  return fma(fma(-p.w, q0, kpi), p.rw, q0);
+}
+
+// one option, walked the way k_price_batch does it: blocks of 128 k, 4 warps of 32 lanes, strike-independent
+// coefficients, four butterfly sums, 8-term rotation segments, partials per warp added in warp order
 static double price_one(const Params& m, double S0, double K, double T, double r, double q, int is_call,
                         int N, double L, double* ab) {
   SetConsts s = make_set_consts(m, r, q);
@@ -19,18 +36,32 @@ static double price_one(const Params& m, double S0, double K, double T, double r
   double a = py_min(a0, sc.x - 0.1), b = py_max(b0, sc.x + 0.1);
   if (ab) { ab[0] = a; ab[1] = b; }
   PassConsts p = make_pass_consts(s, a, b, T);
-  double lane_sum[32];
-  for (int lane = 0; lane < 32; ++lane) {
-    double acc = 0.0;
-    for (int k = lane; k < N; k += 32) {
-      KTerm t = make_kterm(s, p, k);
-      acc += payoff_term(t, p, sc, S0, is_call != 0, k);
+  double sth, cth;
+  fm::sincos_(u_of(p, 1) * (sc.x - p.a), &sth, &cth);
+  double partial[4] = {0, 0, 0, 0};
+  for (int k0 = 0; k0 < N; k0 += 128) {
+    for (int w = 0; w < 4; ++w) {
+      double P[32], Q[32], R[32], a1[32], a2[32], a3[32], g0[32];
+      for (int lane = 0; lane < 32; ++lane) {
+        const int k = k0 + 32 * w + lane;
+        KCoef c; c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
+        if (k < N) c = make_kcoef(make_kterm(s, p, k), p, k);
+        P[lane] = c.P; Q[lane] = c.Q; R[lane] = c.R; a1[lane] = c.a1; a2[lane] = c.a2; a3[lane] = c.P; g0[lane] = c.g0;
+      }
+      const double A1 = butterfly_total(a1), A2 = butterfly_total(a2), A3 = butterfly_total(a3), G0 = butterfly_total(g0);
+      double val[4];
+      for (int sg = 0; sg < 4; ++sg) {
+        const int kstart = k0 + 32 * w + 8 * sg;
+        double sn, cs, spq, sr;
+        fm::sincos_(u_of(p, kstart) * (sc.x - p.a), &sn, &cs);
+        segment_sums(P + 8 * sg, Q + 8 * sg, R + 8 * sg, 8, cs, sn, cth, sth, &spq, &sr);
+        val[sg] = sc.K * sr - (S0 * sc.ex) * spq;
+        if (sg == 0) val[sg] += strike_const_part(is_call != 0, S0, sc.K, sc.x, p, A1, A2, A3, G0);
+      }
+      partial[w] += (val[0] + val[1]) + (val[2] + val[3]);
     }
-    lane_sum[lane] = acc;
   }
-  for (int off = 16; off >= 1; off >>= 1)
-    for (int lane = 0; lane < 32; ++lane) lane_sum[lane] += lane_sum[lane ^ off] * ((lane & off) ? 0.0 : 1.0);
-  return fm::exp_(-r * T) * lane_sum[0];
+  return fm::exp_(-r * T) * (((partial[0] + partial[1]) + partial[2]) + partial[3]);
 }
 
 extern "C" {
