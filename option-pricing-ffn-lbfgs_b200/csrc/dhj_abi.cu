@@ -129,8 +129,9 @@ struct Slot {
 struct dhj_ctx {
   int device = 0;
   int sm_count = 0;
-  int price_blocks_per_sm = 1;
+  int loss_blocks_per_sm = 1;
   int batch_blocks_per_sm = 1;
+  int dense_blocks_per_sm = 1;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   char err[512] = "";
@@ -140,7 +141,7 @@ struct dhj_ctx {
   std::vector<unsigned char> book_image;      // last uploaded packed image (+ strike table) for reuse
   Slot slots[kSlots];
   // loss path
-  DevBuf d_x, d_idx, d_f, d_fg, d_counters, d_prices;
+  DevBuf d_x, d_xv, d_idx, d_f, d_fg, d_counters, d_prices;
   PinBuf h_x, h_res;
   size_t counters_zeroed = 0;
   DevBuf d_peak;
@@ -184,12 +185,6 @@ bool is_pinned_host(const void* p) {
 // k_price_batch handles slices of <= 8 strikes (one thread per k, 32 items per block batch); k_price the rest
 int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_slice, cudaStream_t st);
 
-int price_grid_blocks(const dhj_ctx* ctx, long long items) {
-  long long want = (items + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  long long cap = (long long)ctx->sm_count * ctx->price_blocks_per_sm;
-  return (int)std::max<long long>(1, std::min(want, cap));
-}
-
 int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_slice, cudaStream_t st) {
   const long long items = a.P * (long long)v.n_slices;
   if (max_slice <= kBatchMaxStrikes) {
@@ -205,7 +200,8 @@ int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_s
     }();
     k_price_batch<<<(int)std::max<long long>(1, std::min(batches, cap)), kBatchThreads, extra, st>>>(v, a);
   } else {
-    k_price<<<price_grid_blocks(ctx, items), kThreadsPerBlock, 0, st>>>(v, a);
+    const long long cap = (long long)ctx->sm_count * ctx->dense_blocks_per_sm;
+    k_price_dense<<<(int)std::max<long long>(1, std::min(items, cap)), kBatchThreads, 0, st>>>(v, a);
   }
   DHJ_CUDA(ctx, cudaGetLastError());
   ctx->launches++;
@@ -381,16 +377,19 @@ int dhj_init(int device, dhj_ctx** out) {
   }
   int bps = 0;
   if (e2 == cudaSuccess)
-    e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_price, kThreadsPerBlock, 0);
+    e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_loss_batch, kBatchThreads, 0);
   if (e2 != cudaSuccess) {
     fail(nullptr, DHJ_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e2));
     dhj_destroy(ctx);
     return DHJ_ERR_CUDA;
   }
-  ctx->price_blocks_per_sm = std::max(1, bps);
+  ctx->loss_blocks_per_sm = std::max(1, bps);
   bps = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_price_batch, kBatchThreads, 0) != cudaSuccess) bps = 1;
   ctx->batch_blocks_per_sm = std::max(1, bps);
+  bps = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_price_dense, kBatchThreads, 0) != cudaSuccess) bps = 1;
+  ctx->dense_blocks_per_sm = std::max(1, bps);
   *out = ctx;
   return DHJ_OK;
 }
@@ -406,7 +405,7 @@ int dhj_destroy(dhj_ctx* ctx) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   ctx->d_book.release(); ctx->d_tables.release(); ctx->h_book.release();
-  ctx->d_x.release(); ctx->d_idx.release(); ctx->d_f.release(); ctx->d_fg.release();
+  ctx->d_x.release(); ctx->d_xv.release(); ctx->d_idx.release(); ctx->d_f.release(); ctx->d_fg.release();
   ctx->d_counters.release(); ctx->d_prices.release(); ctx->h_x.release(); ctx->h_res.release();
   ctx->d_peak.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -550,29 +549,62 @@ static int run_loss(dhj_ctx* ctx, const dhj_market* mk, const double* x, const i
   if (rc) return rc;
   if (!out_f || (fd && !out_g)) return fail(ctx, DHJ_ERR_ARG, "null output");
   if (B == 0) return DHJ_OK;
-  const int64_t n_blocks = fd ? B * kFdPoints : B;
-  if (n_blocks > 2147483647LL) return fail(ctx, DHJ_ERR_ARG, "batch too large for one launch");
-  DHJ_CUDA(ctx, ctx->d_f.reserve((size_t)n_blocks * sizeof(double)));
-  LossArgs a;
-  a.x = (const double*)ctx->d_x.p; a.market_index = d_index; a.S0 = (const double*)mk->d_S0.p;
-  a.market = (const double*)mk->d_price.p; a.fd = fd; a.h = h; a.f_all = (double*)ctx->d_f.p;
-  a.fg = nullptr; a.counters = nullptr;
+  const int per = fd ? kFdPoints : 1;
+  const int64_t n_units = B * per;
+  if (n_units > 2000000000LL) return fail(ctx, DHJ_ERR_ARG, "batch too large for one launch");
+  DHJ_CUDA(ctx, ctx->d_f.reserve((size_t)n_units * sizeof(double)));
   size_t res_bytes = (size_t)B * sizeof(double);
   if (fd) {
-    res_bytes = (size_t)B * kFdPoints * sizeof(double);
+    res_bytes = (size_t)n_units * sizeof(double);
     DHJ_CUDA(ctx, ctx->d_fg.reserve(res_bytes));
-    const size_t cb = (size_t)B * sizeof(unsigned int);
-    if (ctx->d_counters.cap < cb || ctx->counters_zeroed < cb) {
-      DHJ_CUDA(ctx, ctx->d_counters.reserve(cb));
-      DHJ_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, ctx->d_counters.cap, ctx->stream));
-      ctx->counters_zeroed = ctx->d_counters.cap;
-    }
-    a.fg = (double*)ctx->d_fg.p; a.counters = (unsigned int*)ctx->d_counters.p;
   }
-  const int warps = std::max(1, std::min(kWarpsPerBlock, mk->view.n_slices));
-  k_loss<<<(unsigned)n_blocks, 32 * warps, 0, ctx->stream>>>(mk->view, a);
-  DHJ_CUDA(ctx, cudaGetLastError());
-  ctx->launches++;
+  const SliceView& v = mk->view;
+  if (mk->book.max_slice <= kBatchMaxStrikes && v.n_slices <= kBatchItems) {
+    // fused path: one launch
+    if (fd) {
+      const size_t cb = (size_t)B * sizeof(unsigned int);
+      if (ctx->d_counters.cap < cb || ctx->counters_zeroed < cb) {
+        DHJ_CUDA(ctx, ctx->d_counters.reserve(cb));
+        DHJ_CUDA(ctx, cudaMemsetAsync(ctx->d_counters.p, 0, ctx->d_counters.cap, ctx->stream));
+        ctx->counters_zeroed = ctx->d_counters.cap;
+      }
+    }
+    LossBatchArgs a;
+    a.x = (const double*)ctx->d_x.p; a.market_index = d_index; a.S0 = (const double*)mk->d_S0.p;
+    a.market = (const double*)mk->d_price.p; a.fd = fd; a.h = h; a.n_units = n_units;
+    a.f_all = (double*)ctx->d_f.p; a.fg = fd ? (double*)ctx->d_fg.p : nullptr;
+    a.counters = fd ? (unsigned int*)ctx->d_counters.p : nullptr;
+    // whole units per block batch; few units (one calibration) -> one unit per block so that every unit
+    // runs on its own SM (latency), many units -> full 32-item batches (throughput)
+    const int upb_max = std::max(1, kBatchItems / v.n_slices);
+    const long long resident = (long long)ctx->sm_count * ctx->loss_blocks_per_sm;
+    a.units_per_batch = (int)std::max<long long>(1, std::min<long long>(upb_max, n_units / resident));
+    const long long batches = (n_units + a.units_per_batch - 1) / a.units_per_batch;
+    k_loss_batch<<<(int)std::max<long long>(1, std::min(batches, resident)), kBatchThreads, 0, ctx->stream>>>(v, a);
+    DHJ_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+  } else {
+    // general path: stencil points -> dense pricing -> reduction
+    DHJ_CUDA(ctx, ctx->d_xv.reserve((size_t)n_units * kNumParams * sizeof(double)));
+    DHJ_CUDA(ctx, ctx->d_idx.reserve((size_t)n_units * sizeof(int)));
+    DHJ_CUDA(ctx, ctx->d_prices.reserve((size_t)n_units * mk->M * sizeof(double)));
+    const unsigned gb = (unsigned)((n_units + 127) / 128);
+    k_fd_expand<<<gb, 128, 0, ctx->stream>>>((const double*)ctx->d_x.p, d_index, B, fd, h, (double*)ctx->d_xv.p,
+                                             (int*)ctx->d_idx.p);
+    DHJ_CUDA(ctx, cudaGetLastError());
+    PriceArgs pa;
+    pa.params = (const double*)ctx->d_xv.p; pa.S0 = (const double*)mk->d_S0.p; pa.s0_stride = 1;
+    pa.row_index = (const int*)ctx->d_idx.p; pa.P = n_units; pa.transform = 1; pa.out = (double*)ctx->d_prices.p;
+    ctx->launches++;
+    rc = launch_price(ctx, v, pa, mk->book.max_slice, ctx->stream);
+    if (rc) return rc;
+    k_loss_reduce<<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(
+        (const double*)ctx->d_prices.p, (const double*)ctx->d_xv.p, (const int*)ctx->d_idx.p,
+        (const double*)mk->d_price.p, mk->M, B, fd, h, (const double*)ctx->d_x.p, (double*)ctx->d_f.p,
+        fd ? (double*)ctx->d_fg.p : nullptr);
+    DHJ_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
   const bool want_all = fd && out_f_all;
   DHJ_CUDA(ctx, ctx->h_res.reserve(res_bytes * (want_all ? 2 : 1)));
   DHJ_CUDA(ctx, cudaMemcpyAsync(ctx->h_res.p, fd ? ctx->d_fg.p : ctx->d_f.p, res_bytes, cudaMemcpyDeviceToHost,

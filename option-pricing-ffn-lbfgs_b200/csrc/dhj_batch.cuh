@@ -59,10 +59,8 @@ __device__ __forceinline__ double u_one(const PassConsts& p) {
 }
 
 // phase 1 for one item, executed by a single thread
-__device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, const double* __restrict__ pp,
-                                             bool transform, double S0, const double* __restrict__ strike_row,
-                                             int s_idx, long long out_row) {
-  const Params m = transform ? transform_params(pp) : load_params(pp);
+__device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, const Params& m, double S0,
+                                             const double* __restrict__ strike_row, int s_idx, long long out_row) {
   rec.set = make_set_consts(m, v.r, v.q);
   const double T = v.slice_T[s_idx];
   double a0, b0;

@@ -1,18 +1,20 @@
 // dhj_kernels.cuh — the CUDA kernels of libdhj.so (sm_100a).
 //
-//   k_price      one warp per (parameter set, maturity slice): prices -> HBM        (K1 / K3 of SURVEY §2)
-//   k_loss       one block per loss evaluation: exp/tanh transform, prices of every market option,
-//                relative-MSE + Feller penalty + 1e10 sentinel; in FD mode the 14 evaluations of one
-//                optimiser state are 14 blocks and the last one to finish assembles the gradient (K2)
-//   k_fp64_peak  DFMA-chain probe for the FP64 roofline denominator
+//   k_price_batch  slices of <= 8 strikes: thread per cosine index, 32 items per block batch   (K1 / K3 of SURVEY §2)
+//   k_price_dense  many strikes per slice: block per item, lane per strike
+//   k_loss_batch   K2: exp/tanh transform + prices of every market option + relative-MSE + Feller penalty +
+//                  1e10 sentinel; in FD mode the 14 stencil points of an optimiser state are 14 units and the
+//                  thread that finishes the last one assembles scipy's gradient — ONE launch per optimiser step
+//   k_fd_expand / k_loss_reduce  general fallback of K2 around k_price_dense
+//   k_cf / k_truncation_range / k_chi_psi  the remaining public methods of DoubleHeston
+//   k_fp64_peak    DFMA-chain probe for the FP64 roofline denominator
 #pragma once
 #include "dhj_engine.cuh"
 #include "dhj_batch.cuh"
+#include "dhj_dense.cuh"
 
 namespace dhj {
 
-constexpr int kWarpsPerBlock = 4;
-constexpr int kThreadsPerBlock = 32 * kWarpsPerBlock;
 constexpr int kFdPoints = kNumParams + 1;      // f(x) and 13 forward points
 constexpr double kSentinel = 1e10;             // lbfgs_calibrator.py:152-153
 
@@ -25,26 +27,6 @@ struct PriceArgs {
   int transform;
   double* out;               // [P][M]
 };
-
-__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_price(SliceView v, PriceArgs a) {
-  __shared__ WarpSmem ws_all[kWarpsPerBlock];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  WarpSmem& ws = ws_all[warp];
-  const long long n_items = a.P * (long long)v.n_slices;
-  const long long stride = (long long)gridDim.x * kWarpsPerBlock;
-  for (long long item = (long long)blockIdx.x * kWarpsPerBlock + warp; item < n_items; item += stride) {
-    const long long p = item / v.n_slices;
-    const int s = (int)(item - p * v.n_slices);
-    const long long row = a.row_index ? (long long)a.row_index[p] : p;
-    const double* pp = a.params + kNumParams * p;
-    const Params m = a.transform ? transform_params(pp) : load_params(pp);
-    const double S0 = a.S0[row * a.s0_stride];
-    const double* strike_row = v.strike + row * v.strike_stride;
-    double* out_row = a.out + p * (long long)v.n_options;
-    price_slice(ws, m, v, s, S0, strike_row, lane,
-                [&](int o, double price) { out_row[v.pos[o]] = price; });
-  }
-}
 
 // Throughput variant of k_price for slices of <= 8 strikes: see dhj_batch.cuh.
 __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(SliceView v, PriceArgs a) {
@@ -61,8 +43,10 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
       const long long p = item / v.n_slices;
       const int s = (int)(item - p * v.n_slices);
       const long long row = a.row_index ? (long long)a.row_index[p] : p;
-      prepare_item(sm.items[tid], v, a.params + kNumParams * p, a.transform != 0, a.S0[row * a.s0_stride],
-                   v.strike + row * v.strike_stride, s, p * (long long)v.n_options);
+      const double* pp = a.params + kNumParams * p;
+      const Params m = a.transform ? transform_params(pp) : load_params(pp);
+      prepare_item(sm.items[tid], v, m, a.S0[row * a.s0_stride], v.strike + row * v.strike_stride, s,
+                   p * (long long)v.n_options);
     }
     __syncthreads();
     // ---- phase 2: one thread per cosine index ----------------------------------------------------
@@ -105,82 +89,241 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
   }
 }
 
-struct LossArgs {
-  const double* x;           // [B][13] unconstrained
-  const int* market_index;   // optional [B] (FD mode: [C])
-  const double* S0;          // [n_markets]
-  const double* market;      // [n_markets][M] caller order
-  int fd;                    // 0: one block per x ; 1: 14 blocks per x
-  double h;
-  double* f_all;             // [B] (fd: [C][14] scratch)
-  double* fg;                // fd: [C][14] = f, g[13]
-  unsigned int* counters;    // fd: [C], zero on entry, zero on exit
-};
-
-__global__ void __launch_bounds__(kThreadsPerBlock, 4) k_loss(SliceView v, LossArgs a) {
-  __shared__ WarpSmem ws_all[kWarpsPerBlock];
-  __shared__ double red_sq[kWarpsPerBlock];
-  __shared__ int red_bad[kWarpsPerBlock];
-  __shared__ int is_last;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_warps = blockDim.x >> 5;
-  const long long b = blockIdx.x;
-  const long long c = a.fd ? b / kFdPoints : b;
-  const int var = a.fd ? (int)(b - c * kFdPoints) : 0;
-
-  double xv[kNumParams];
+// Many strikes per slice: one block per item, lane per strike (dhj_dense.cuh).
+__global__ void __launch_bounds__(kBatchThreads, 4) k_price_dense(SliceView v, PriceArgs a) {
+  __shared__ DenseSmem sm;
+  const int tid = threadIdx.x;
+  const long long n_items = a.P * (long long)v.n_slices;
+  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const long long p = item / v.n_slices;
+    const int s = (int)(item - p * v.n_slices);
+    const long long row = a.row_index ? (long long)a.row_index[p] : p;
+    const double* strike_row = v.strike + row * v.strike_stride;
+    const int o_lo = v.slice_off[s], o_hi = v.slice_off[s + 1];
+    __syncthreads();                                   // previous item has left shared memory
+    if (tid == 0) {
+      const double* pp = a.params + kNumParams * p;
+      const Params m = a.transform ? transform_params(pp) : load_params(pp);
+      sm.set = make_set_consts(m, v.r, v.q);
+      const double T = v.slice_T[s];
+      truncation_range(m, T, v.r, v.L, &sm.a0, &sm.b0);
+      sm.pass = make_pass_consts(sm.set, sm.a0, sm.b0, T);
+      sm.S0 = a.S0[row * a.s0_stride];
+      sm.disc = fm::exp_(-v.r * T);
+    }
+    __syncthreads();
+    for (int c_lo = o_lo; c_lo < o_hi; c_lo += kDenseChunk) {
+      const int cnt = min(kDenseChunk, o_hi - c_lo);
+      if (tid == 0) sm.n_bind = 0;
+      __syncthreads();
+      const double u1 = u_one(sm.pass);
+      for (int t = tid; t < cnt; t += kBatchThreads) {
+        double K = strike_row[v.pos[c_lo + t]];
+        if (v.scale_by_spot) K = K * sm.S0 / 100.0;
+        const StrikeConsts sc = make_strike_consts(K, sm.S0);
+        sm.K[t] = sc.K; sm.x[t] = sc.x; sm.ex[t] = sc.ex;
+        fm::sincos_(u1 * (sc.x - sm.a0), &sm.sth[t], &sm.cth[t]);
+        const bool bind = ((sc.x - 0.1) < sm.a0) || ((sc.x + 0.1) > sm.b0);
+        sm.bind[t] = bind; sm.call[t] = v.call[c_lo + t];
+        if (bind) atomicAdd(&sm.n_bind, 1);
 #pragma unroll
-  for (int i = 0; i < kNumParams; ++i) xv[i] = a.x[kNumParams * c + i];
-  // scipy's forward point: x_i + h  (_numdiff.py _dense_difference, h = abs_step)
-#pragma unroll
-  for (int i = 0; i < kNumParams; ++i)
-    if (var == i + 1) xv[i] = xv[i] + a.h;
-  const Params m = transform_params(xv);
-  const long long mi = a.market_index ? a.market_index[c] : 0;
-  const double S0 = a.S0[mi];
-  const double* strike_row = v.strike + mi * v.strike_stride;
-  const double* market_row = a.market + mi * (long long)v.n_options;
-
-  double sq = 0.0;
-  int bad = 0;
-  for (int s = warp; s < v.n_slices; s += n_warps) {
-    price_slice(ws_all[warp], m, v, s, S0, strike_row, lane, [&](int o, double price) {
-      // lbfgs_calibrator.py:152: isnan or isinf or <= 0
-      if (!(price > 0.0) || isinf(price)) bad = 1;
-      const double mk = market_row[v.pos[o]];
-      const double rel = (price - mk) / mk;               // :163
-      sq += rel * rel;
-    });
-  }
-  sq = warp_sum(sq);
-  bad = __any_sync(kFullMask, bad);
-  if (lane == 0) { red_sq[warp] = sq; red_bad[warp] = bad; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    int any_bad = 0;
-    for (int w = 0; w < n_warps; ++w) { tot += red_sq[w]; any_bad |= red_bad[w]; }
-    const double loss = any_bad ? kSentinel : tot / (double)v.n_options + feller_penalty(m);   // :164-169
-    a.f_all[b] = loss;
-    if (a.fd) {
-      __threadfence();
-      const unsigned prev = atomicAdd(&a.counters[c], 1u);
-      is_last = (prev == (unsigned)(kFdPoints - 1));
+        for (int w = 0; w < kBatchWarps; ++w) sm.partial[w][t] = 0.0;
+      }
+      __syncthreads();
+      if (sm.n_bind < cnt) dense_pass(sm, sm.pass, sm.cth, sm.sth, cnt, -1, v.n_cos, tid);
+      if (sm.n_bind > 0) {
+        for (int t = 0; t < cnt; ++t) {
+          if (!sm.bind[t]) continue;                   // uniform: flags live in shared memory
+          __syncthreads();
+          if (tid == 0) {
+            sm.extra_pass = make_pass_consts(sm.set, py_min(sm.a0, sm.x[t] - 0.1), py_max(sm.b0, sm.x[t] + 0.1),
+                                             sm.pass.T);
+            fm::sincos_(u_one(sm.extra_pass) * (sm.x[t] - sm.extra_pass.a), &sm.extra_sth, &sm.extra_cth);
+          }
+          __syncthreads();
+          dense_pass(sm, sm.extra_pass, &sm.extra_cth, &sm.extra_sth, cnt, t, v.n_cos, tid);
+        }
+      }
+      __syncthreads();
+      double* out_row = a.out + p * (long long)v.n_options;
+      for (int t = tid; t < cnt; t += kBatchThreads) {
+        const double sum = ((sm.partial[0][t] + sm.partial[1][t]) + sm.partial[2][t]) + sm.partial[3][t];
+        out_row[v.pos[c_lo + t]] = sm.disc * sum;
+      }
+      __syncthreads();
     }
   }
-  if (!a.fd) return;
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    const double* f = a.f_all + kFdPoints * c;
-    if (threadIdx.x < kNumParams) {
-      const int i = threadIdx.x;
-      const double xi = a.x[kNumParams * c + i];
-      const double dx = (xi + a.h) - xi;
-      a.fg[kFdPoints * c + 1 + i] = (__ldcg(f + 1 + i) - __ldcg(f)) / dx;
-    } else if (threadIdx.x == kNumParams) {
-      a.fg[kFdPoints * c] = __ldcg(f);
-      a.counters[c] = 0u;
+}
+
+// Fused loss kernel on the batch engine (slices of <= 8 strikes, <= 32 slices): a "unit" is one loss evaluation
+// (one x; in FD mode one of the 14 stencil points of an optimiser state); a block batch holds
+// `units_per_batch` whole units (= units_per_batch * n_slices <= 32 items), prices them as k_price_batch does,
+// then one thread per unit forms mean(rel^2) + Feller / the 1e10 sentinel, and the thread that completes a
+// state's 14th point assembles scipy's forward-difference gradient.
+struct LossBatchArgs {
+  const double* x;           // [B][13] (fd: [C][13]) unconstrained
+  const int* market_index;   // optional, per x
+  const double* S0;          // [n_markets]
+  const double* market;      // [n_markets][M] caller order
+  int fd;
+  double h;
+  long long n_units;         // B, or C*14
+  int units_per_batch;
+  double* f_all;             // [n_units]
+  double* fg;                // fd: [C][14]
+  unsigned int* counters;    // fd: [C]
+};
+
+__global__ void __launch_bounds__(kBatchThreads, 4) k_loss_batch(SliceView v, LossBatchArgs a) {
+  __shared__ BatchSmem sm;
+  __shared__ double s_price[kBatchItems][kBatchMaxStrikes];
+  __shared__ double s_feller[kBatchItems];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nS = v.n_slices;
+  const long long n_batches = (a.n_units + a.units_per_batch - 1) / a.units_per_batch;
+  for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    const long long base_unit = batch * a.units_per_batch;
+    const int n_units_here = (int)min((long long)a.units_per_batch, a.n_units - base_unit);
+    const int cnt_items = n_units_here * nS;
+    // ---- phase 1 -----------------------------------------------------------------------------------
+    if (tid < cnt_items) {
+      const int ul = tid / nS, s = tid - ul * nS;
+      const long long unit = base_unit + ul;
+      const long long c = a.fd ? unit / kFdPoints : unit;
+      const int var = a.fd ? (int)(unit - c * kFdPoints) : 0;
+      double xv[kNumParams];
+#pragma unroll
+      for (int i = 0; i < kNumParams; ++i) xv[i] = a.x[kNumParams * c + i];
+#pragma unroll
+      for (int i = 0; i < kNumParams; ++i)
+        if (var == i + 1) xv[i] = xv[i] + a.h;         // scipy's forward point x_i + h
+      const Params m = transform_params(xv);
+      const long long mi = a.market_index ? a.market_index[c] : 0;
+      prepare_item(sm.items[tid], v, m, a.S0[mi], v.strike + mi * v.strike_stride, s, mi * (long long)v.n_options);
+      if (s == 0) s_feller[ul] = feller_penalty(m);
+    }
+    __syncthreads();
+    // ---- phase 2 (identical to k_price_batch) --------------------------------------------------------
+#pragma unroll 1
+    for (int i = 0; i < cnt_items; ++i) {
+      const ItemRec& it = sm.items[i];
+      double* warp_partial = sm.partial[i][warp];
+      if (lane < kBatchMaxStrikes) warp_partial[lane] = 0.0;
+      __syncwarp();
+      const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
+      if (reg_mask) contract_pass(it, it.pass, it.cth, it.sth, reg_mask, v.n_cos, tid, sm.stage[warp], warp_partial);
+      unsigned todo = it.valid_mask & it.bind_mask;
+      while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        __syncthreads();
+        if (tid == 0) {
+          sm.extra_pass = make_pass_consts(it.set, py_min(it.a0, it.x[j] - 0.1), py_max(it.b0, it.x[j] + 0.1),
+                                           it.pass.T);
+          fm::sincos_(u_one(sm.extra_pass) * (it.x[j] - sm.extra_pass.a), &sm.extra_sth, &sm.extra_cth);
+        }
+        __syncthreads();
+        contract_pass(it, sm.extra_pass, &sm.extra_cth - j, &sm.extra_sth - j, 1u << j, v.n_cos, tid, sm.stage[warp],
+                      warp_partial);
+      }
+    }
+    __syncthreads();
+    // ---- phase 3: prices -> shared memory --------------------------------------------------------------
+    for (int t = tid; t < cnt_items * kBatchMaxStrikes; t += kBatchThreads) {
+      const int i = t / kBatchMaxStrikes, j = t - i * kBatchMaxStrikes;
+      const ItemRec& it = sm.items[i];
+      if (it.valid_mask & (1u << j)) {
+        const double* q = sm.partial[i][0] + j;
+        s_price[i][j] = it.disc * (((q[0] + q[kBatchMaxStrikes]) + q[2 * kBatchMaxStrikes]) + q[3 * kBatchMaxStrikes]);
+      }
+    }
+    __syncthreads();
+    // ---- phase 4: one thread per unit: loss, and the gradient when a state's stencil is complete ----------
+    if (tid < n_units_here) {
+      const long long unit = base_unit + tid;
+      const long long c = a.fd ? unit / kFdPoints : unit;
+      double sq = 0.0;
+      bool bad = false;
+      for (int s = 0; s < nS; ++s) {
+        const ItemRec& it = sm.items[tid * nS + s];
+        const double* market_row = a.market + it.out_row;           // out_row = market index * M
+        const int cnt = __popc(it.valid_mask);
+        for (int j = 0; j < cnt; ++j) {
+          const double price = s_price[tid * nS + s][j];
+          if (!(price > 0.0) || isinf(price)) bad = true;           // lbfgs_calibrator.py:152
+          const double mk = market_row[v.pos[it.o_lo + j]];
+          const double rel = (price - mk) / mk;                     // :163
+          sq += rel * rel;
+        }
+      }
+      const double loss = bad ? kSentinel : sq / (double)v.n_options + s_feller[tid];   // :164-169
+      a.f_all[unit] = loss;
+      if (a.fd) {
+        __threadfence();
+        const unsigned prev = atomicAdd(&a.counters[c], 1u);
+        if (prev == (unsigned)(kFdPoints - 1)) {
+          __threadfence();
+          const double* f = a.f_all + kFdPoints * c;
+          const double f0 = __ldcg(f);
+          a.fg[kFdPoints * c] = f0;
+          for (int i = 0; i < kNumParams; ++i) {
+            const double xi = a.x[kNumParams * c + i];
+            const double dx = (xi + a.h) - xi;
+            a.fg[kFdPoints * c + 1 + i] = (__ldcg(f + 1 + i) - f0) / dx;
+          }
+          a.counters[c] = 0u;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// General loss path (slices with more than 8 strikes or more than 32 slices): k_fd_expand builds the stencil
+// points, k_price_dense prices them (transform on), k_loss_reduce forms the losses and gradients.
+__global__ void k_fd_expand(const double* __restrict__ x, const int* __restrict__ market_index, long long n_x, int fd,
+                            double h, double* __restrict__ xv, int* __restrict__ row_index) {
+  const long long unit = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = fd ? kFdPoints : 1;
+  if (unit >= n_x * per) return;
+  const long long c = unit / per;
+  const int var = (int)(unit - c * per);
+  for (int i = 0; i < kNumParams; ++i) {
+    const double xi = x[kNumParams * c + i];
+    xv[kNumParams * unit + i] = (var == i + 1) ? xi + h : xi;
+  }
+  row_index[unit] = market_index ? market_index[c] : 0;
+}
+
+__global__ void k_loss_reduce(const double* __restrict__ prices, const double* __restrict__ xv,
+                              const int* __restrict__ row_index, const double* __restrict__ market, int M,
+                              long long n_x, int fd, double h, const double* __restrict__ x,
+                              double* __restrict__ f_all, double* __restrict__ fg) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_x) return;
+  const int per = fd ? kFdPoints : 1;
+  double f0 = 0.0;
+  for (int var = 0; var < per; ++var) {
+    const long long unit = c * per + var;
+    const double* pr = prices + unit * M;
+    const double* mk = market + (long long)row_index[unit] * M;
+    double sq = 0.0;
+    bool bad = false;
+    for (int o = 0; o < M; ++o) {
+      const double price = pr[o];
+      if (!(price > 0.0) || isinf(price)) bad = true;
+      const double rel = (price - mk[o]) / mk[o];
+      sq += rel * rel;
+    }
+    const Params m = transform_params(xv + kNumParams * unit);
+    const double loss = bad ? kSentinel : sq / (double)M + feller_penalty(m);
+    f_all[unit] = loss;
+    if (fd) {
+      if (var == 0) { f0 = loss; fg[kFdPoints * c] = loss; }
+      else {
+        const double xi = x[kNumParams * c + var - 1];
+        fg[kFdPoints * c + var] = (loss - f0) / ((xi + h) - xi);
+      }
     }
   }
 }

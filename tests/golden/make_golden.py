@@ -21,6 +21,7 @@ Fixtures (all float64, written with numpy.savez so values round-trip bit-exactly
                        the 14-evaluation forward-difference stencil scipy uses (lbfgs_calibrator.py:118-177)
   initial_guess.npz    get_initial_guess(0/1/2) under np.random.seed(0) (lbfgs_calibrator.py:179-234)
   generator_seed42.npz generate_synthetic_calibrations(20) under np.random.seed(42)
+  calib_ensemble.npz   (--slow) final losses of the reference from ulp-perturbed copies of start 1's x0
   calib_trajectory.npz (--slow) every x the reference optimiser visits for the C1 market,
                        np.random.seed(0), starts 0..2, with losses, nit, messages
 """
@@ -326,6 +327,33 @@ def make_calib_trajectory():
          wall_seconds=time.time() - t00, **out)
 
 
+def _ensemble_member(k):
+    """Reference optimiser from start 1's x0 scaled by (1 + k * 2^-52): SURVEY H1's noise-floor probe."""
+    from scipy.optimize import minimize
+    spot, r, opts = c1_market()
+    np.random.seed(0)
+    cal = DoubleHestonJumpCalibrator(spot, r, opts)
+    x0 = cal.get_initial_guess(1) * (1.0 + k * 2.0 ** -52)
+    res = minimize(fun=cal.compute_loss, x0=x0, method="L-BFGS-B",
+                   options={"maxiter": 300, "ftol": 1e-9, "gtol": 1e-6, "disp": False})
+    return k, float(res.fun), int(res.nit), int(res.nfev), str(res.message)
+
+
+def make_calib_ensemble():
+    """Final losses of the REFERENCE for 1-ulp-level perturbations of the start-1 initial point (C1 market,
+    np.random.seed(0)): the spread the reference shows against itself, which any other FP64 implementation
+    (different libm, different summation order) necessarily falls into."""
+    import multiprocessing as mp
+    ks = [-3, -2, -1, 0, 1, 2, 3, 5]
+    with mp.get_context("fork").Pool(len(ks)) as pool:
+        out = pool.map(_ensemble_member, ks)
+    for row in out:
+        print(row, flush=True)
+    save("calib_ensemble.npz", k=np.array([o[0] for o in out]), fun=np.array([o[1] for o in out]),
+         nit=np.array([o[2] for o in out]), nfev=np.array([o[3] for o in out]),
+         message=np.array([o[4] for o in out]))
+
+
 MAKERS = {
     "known_answers": make_known_answers,
     "prices_grid15": make_prices_grid15,
@@ -336,7 +364,7 @@ MAKERS = {
     "initial_guess": make_initial_guess,
     "generator": make_generator,
 }
-SLOW = {"calib_trajectory": make_calib_trajectory}
+SLOW = {"calib_trajectory": make_calib_trajectory, "calib_ensemble": make_calib_ensemble}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -221,3 +221,41 @@ def test_many_markets(ctx):
     f, grad = mk.loss_fd(x, 1e-8, idx)
     assert np.abs(f - got).max() == 0.0
     mk.close()
+
+
+def test_loss_general_path(ctx):
+    """A market with 12 strikes on one maturity (> 8 per slice) takes the expand / dense-price / reduce path."""
+    rng = np.random.default_rng(9)
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=13)
+    K = np.concatenate([np.linspace(85, 115, 12), [95.0, 100.0, 105.0]])
+    T = np.concatenate([np.full(12, 0.5), np.full(3, 1.0)])
+    call = np.concatenate([np.ones(12), [0, 1, 0]])
+    market = O.price_batch(params, 100.0, K, T, call, 0.02)[0] * (1 + 0.01 * rng.standard_normal(15))
+    mk = ctx.market(100.0, 0.02, K, T, call, market)
+    x = O.inverse_transform_params(params)[None, :] + 0.1 * rng.standard_normal((5, 13))
+    got = mk.loss_batch(x)
+    want = O.loss_batch(x, 100.0, 0.02, K, T, call, market)
+    assert np.abs(got - want).max() <= LOSS_ATOL
+    f, grad, f_all = mk.loss_fd(x, 1e-8, want_all=True)
+    assert np.array_equal(f, got)
+    for c in range(5):
+        dx = (x[c] + 1e-8) - x[c]
+        assert np.array_equal(grad[c], (f_all[c, 1:] - f_all[c, 0]) / dx)
+        pts, _ = O.fd_stencil(x[c])
+        assert np.abs(f_all[c] - O.loss_batch(pts, 100.0, 0.02, K, T, call, market)).max() <= LOSS_ATOL
+    assert rel_err(mk.prices(x), O.price_batch(O.transform_params(x), 100.0, K, T, call, 0.02)).max() <= PRICE_RTOL
+    mk.close()
+
+
+def test_many_strikes_and_slices(ctx):
+    """300 strikes on one slice (two 256-strike chunks) and 40 maturities (more slices than a block batch)."""
+    rng = np.random.default_rng(10)
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(3, 13))
+    K = np.linspace(70, 130, 300); T = np.full(300, 0.75)
+    call = (np.arange(300) % 3 != 0).astype(int)
+    got = ctx.price_list(params, 100.0, K, T, call, 0.03)
+    want = O.price_batch(params, 100.0, K, T, call, 0.03)
+    assert (np.abs(got - want) <= 1e-10 * np.abs(want) + 1e-12).all()
+    T2 = np.linspace(0.1, 2.0, 40); K2 = np.full(40, 100.0)
+    got2 = ctx.price_list(params, 100.0, K2, T2, np.ones(40), 0.03)
+    assert rel_err(got2, O.price_batch(params, 100.0, K2, T2, np.ones(40), 0.03)).max() <= PRICE_RTOL
