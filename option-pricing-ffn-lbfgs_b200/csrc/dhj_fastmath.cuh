@@ -107,23 +107,56 @@ DHJ_FM void sqrt_rsqrt(double x, double* s_out, double* y_out) {
 }
 DHJ_FM double sqrt_(double x) { double s, y; sqrt_rsqrt(x, &s, &y); return s; }
 
+// scalar constants live in constant memory too: as literals every use costs two IMAD.MOV (2 issue cycles each
+// on B200) to build the 64-bit immediate; from the constant bank it is one load
+struct ScalarConsts {
+  double TwoOverPi;
+  double Pio2Hi;
+  double Pio2Mid;
+  double Log2e;
+  double Ln2Hi;
+  double Ln2Lo;
+  double Ln2HiFull;
+  double Ln2LoFull;
+  double Sqrt2;
+  double SqrtHalf;
+  double TanPi8;
+  double PiO4;
+  double PiO4Lo;
+  double PiO2;
+  double PiD;
+};
+DHJ_CONSTANT ScalarConsts kS = {
+  6.36619772367581382433e-01,
+  1.57079632679489655800e+00,
+  6.12323399573676603587e-17,
+  1.44269504088896338700e+00,
+  6.93147180369123816490e-01,
+  1.90821492927058770002e-10,
+  6.93147180559945286227e-01,
+  2.31904681384629955842e-17,
+  1.41421356237309514547e+00,
+  7.07106781186547572737e-01,
+  4.14213562373095048802e-01,
+  7.85398163397448278999e-01,
+  3.06161699786838301793e-17,
+  1.57079632679489655800e+00,
+  3.14159265358979311600e+00};
+
 // ---- sincos ----------------------------------------------------------------------------------------
 DHJ_CONSTANT double kSin[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
                                2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
 DHJ_CONSTANT double kCos[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
                                -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
-constexpr double kTwoOverPi = 6.36619772367581382433e-01;
-constexpr double kPio2Hi = 1.57079632679489655800e+00;
-constexpr double kPio2Mid = 6.12323399573676603587e-17;
 constexpr double kRoundMagic = 6755399441055744.0;     // 1.5 * 2^52: (x + magic) - magic = rint(x), low word = int
 
 // sin and cos of x, |x| <= ~1e5 (Cody-Waite with FMA; no Payne-Hanek path)
 DHJ_FM void sincos_(double x, double* s_out, double* c_out) {
-  const double t = fma(x, kTwoOverPi, kRoundMagic);
+  const double t = fma(x, kS.TwoOverPi, kRoundMagic);
   const int q = lo32(t);
   const double n = t - kRoundMagic;
-  double r = fma(-n, kPio2Hi, x);
-  r = fma(-n, kPio2Mid, r);               // |n| < 2^17: the next term of pi/2 (1.5e-33 n) is far below 1 ulp
+  double r = fma(-n, kS.Pio2Hi, x);
+  r = fma(-n, kS.Pio2Mid, r);               // |n| < 2^17: the next term of pi/2 (1.5e-33 n) is far below 1 ulp
   const double z = r * r;
   double ps = kSin[5];
   ps = fma(ps, z, kSin[4]); ps = fma(ps, z, kSin[3]); ps = fma(ps, z, kSin[2]); ps = fma(ps, z, kSin[1]);
@@ -148,37 +181,33 @@ DHJ_CONSTANT double kExpQ[10] = {0.50000000000000010212, 0.16666666666666674523,
                                  0.0083333333333222152106, 0.001388888891719838631, 0.00019841269886566398025,
                                  0.00002480152132015615238, 2.7557242364849317814e-6, 2.7620076799169896683e-7,
                                  2.5110039179932520501e-8};
-constexpr double kLog2e = 1.44269504088896338700e+00;
-constexpr double kLn2Hi = 6.93147180369123816490e-01;    // fdlibm split: hi has 32 significant bits
-constexpr double kLn2Lo = 1.90821492927058770002e-10;
 
-// core: p * 2^n, valid for -1400 < x < 1400 (no guards)
+// core: p * 2^n with p in [0.70, 1.42]: n is added to p's exponent field (one integer add instead of building
+// 2^n and multiplying).  Valid while the result is a normal number: -708 < x < 709.7; callers guard the rest.
 DHJ_FM double exp_core(double x) {
-  const double t = fma(x, kLog2e, kRoundMagic);
+  const double t = fma(x, kS.Log2e, kRoundMagic);
   const int n = lo32(t);
   const double nf = t - kRoundMagic;
-  double r = fma(-nf, kLn2Hi, x);
-  r = fma(-nf, kLn2Lo, r);
+  double r = fma(-nf, kS.Ln2Hi, x);
+  r = fma(-nf, kS.Ln2Lo, r);
   double q = kExpQ[9];
   q = fma(q, r, kExpQ[8]); q = fma(q, r, kExpQ[7]); q = fma(q, r, kExpQ[6]); q = fma(q, r, kExpQ[5]);
   q = fma(q, r, kExpQ[4]); q = fma(q, r, kExpQ[3]); q = fma(q, r, kExpQ[2]); q = fma(q, r, kExpQ[1]);
   q = fma(q, r, kExpQ[0]);
   const double p = 1.0 + fma(r * r, q, r);
-  // 2^n in two factors so that results down to the smallest normal and up to DBL_MAX are exact scalings
-  const int n1 = n >> 1, n2 = n - n1;
-  return (p * from_hilo((n1 + 1023) << 20, 0)) * from_hilo((n2 + 1023) << 20, 0);
+  return from_hilo(hi32(p) + (n << 20), lo32(p));
 }
 // full range
 DHJ_FM double exp_(double x) {
   double res = exp_core(x);
-  res = (x < -745.2) ? 0.0 : res;
-  res = (x > 709.79) ? (double)INFINITY : res;
+  res = (x < -708.0) ? 0.0 : res;          // results below the smallest normal are flushed to zero
+  res = (x > 709.7) ? (double)INFINITY : res;
   return res;
 }
 // for arguments known to be <= ~700 (decay factors): only the underflow side is guarded
 DHJ_FM double exp_neg(double x) {
   const double res = exp_core(x);
-  return (x < -745.2) ? 0.0 : res;
+  return (x < -708.0) ? 0.0 : res;
 }
 
 // ---- log of a ratio --------------------------------------------------------------------------------
@@ -187,16 +216,12 @@ DHJ_FM double exp_neg(double x) {
 DHJ_CONSTANT double kLg[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
                               2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
                               1.479819860511658591e-01};
-constexpr double kLn2HiFull = 6.93147180559945286227e-01;   // ln2 rounded to double
-constexpr double kLn2LoFull = 2.31904681384629955842e-17;   // ln2 - kLn2HiFull
-constexpr double kSqrt2 = 1.41421356237309514547e+00;
-constexpr double kSqrtHalf = 7.07106781186547572737e-01;
 
 DHJ_FM double log_ratio(double a, double b) {
   // align exponents: b' = b * 2^(ea - eb) has the exponent of a, so a/b' in (1/2, 2)
   int k = ((hi32(a) >> 20) & 0x7ff) - ((hi32(b) >> 20) & 0x7ff);
   double bs = from_hilo(hi32(b) + (k << 20), lo32(b));
-  const bool up = a > kSqrt2 * bs, down = a < kSqrtHalf * bs;
+  const bool up = a > kS.Sqrt2 * bs, down = a < kS.SqrtHalf * bs;
   bs = up ? 2.0 * bs : (down ? 0.5 * bs : bs);
   k += up ? 1 : (down ? -1 : 0);
   const double s = div(a - bs, a + bs);
@@ -207,7 +232,7 @@ DHJ_FM double log_ratio(double a, double b) {
   R = R * z;
   const double kf = (double)k;
   // k ln2 + 2s + s R, low-order parts first
-  const double res = fma(kf, kLn2HiFull, fma(s, R, fma(kf, kLn2LoFull, s + s)));
+  const double res = fma(kf, kS.Ln2HiFull, fma(s, R, fma(kf, kS.Ln2LoFull, s + s)));
   const double nan_probe = a + b;          // the exponent surgery above would launder a NaN b
   return (nan_probe != nan_probe) ? nan_probe : res;
 }
@@ -219,18 +244,13 @@ DHJ_CONSTANT double kAt[11] = {3.33333333333329318027e-01, -1.999999999987648324
                                -1.11111104054623557880e-01, 9.09088713343650656196e-02, -7.69187620504482999495e-02,
                                6.66107313738753120669e-02, -5.83357013379057348645e-02, 4.97687799461593236017e-02,
                                -3.65315727442169155270e-02, 1.62858201153657823623e-02};
-constexpr double kTanPi8 = 4.14213562373095048802e-01;
-constexpr double kPiO4 = 7.85398163397448278999e-01;
-constexpr double kPiO4Lo = 3.06161699786838301793e-17;
-constexpr double kPiO2 = 1.57079632679489655800e+00;
-constexpr double kPiD = 3.14159265358979311600e+00;
 
 DHJ_FM double atan2_(double y, double x) {
   const double ax = fabs(x), ay = fabs(y);
   const bool steep = ay > ax;                       // NaN-safe: a NaN operand lands in mn or mx and propagates
   const double mx = steep ? ay : ax, mn = steep ? ax : ay;
   // octant reduction without a second division: atan(mn/mx) = pi/4 + atan((mn-mx)/(mn+mx)) when mn/mx > tan(pi/8)
-  const bool hi = mn > kTanPi8 * mx;
+  const bool hi = mn > kS.TanPi8 * mx;
   const double num = hi ? mn - mx : mn;
   const double den = hi ? mn + mx : mx;
   const double t = div(num, den);
@@ -239,10 +259,10 @@ DHJ_FM double atan2_(double y, double x) {
   p = fma(p, z, kAt[9]); p = fma(p, z, kAt[8]); p = fma(p, z, kAt[7]); p = fma(p, z, kAt[6]); p = fma(p, z, kAt[5]);
   p = fma(p, z, kAt[4]); p = fma(p, z, kAt[3]); p = fma(p, z, kAt[2]); p = fma(p, z, kAt[1]); p = fma(p, z, kAt[0]);
   double r = fma(-(t * z), p, t);
-  r = hi ? (r + kPiO4Lo) + kPiO4 : r;     // atan(mn/mx) in [0, pi/4]
-  r = steep ? kPiO2 - r : r;              // first quadrant angle
-  r = (x < 0.0) ? kPiD - r : r;
-  r = (mx == 0.0) ? ((x < 0.0 || (x == 0.0 && signbit(x))) ? kPiD : 0.0) : r;   // atan2(+-0, +-0)
+  r = hi ? (r + kS.PiO4Lo) + kS.PiO4 : r;     // atan(mn/mx) in [0, pi/4]
+  r = steep ? kS.PiO2 - r : r;              // first quadrant angle
+  r = (x < 0.0) ? kS.PiD - r : r;
+  r = (mx == 0.0) ? ((x < 0.0 || (x == 0.0 && signbit(x))) ? kS.PiD : 0.0) : r;   // atan2(+-0, +-0)
   return copysign(r, y);
 }
 

@@ -195,21 +195,22 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) 
   const double Er = er * cs, Ei = er * sn;
   const double mr = kap - dr, mi = bi - di;         // beta - d
   const double pr = kap + dr, pi_ = bi + di;        // beta + d
-  // D = pl - m*E
-  const double Dr = pr - (mr * Er - mi * Ei);
-  const double Di = pi_ - (mr * Ei + mi * Er);
+  // D = pl - m*E   (from here on complex products are written with FMAs: nothing below is an operand the
+  // reference rounds separately in the same form, and an FP64 instruction is what the kernel is short of)
+  const double Dr = fma(-mr, Er, fma(mi, Ei, pr));
+  const double Di = fma(-mr, Ei, fma(-mi, Er, pi_));
   const double nD = fma(Dr, Dr, Di * Di);
   const double inD = fm::rcp(nD);
   // Q = (1-E) * pl / D = (1-E) * pl * conj(D) / |D|^2
   const double ar = 1.0 - Er, ai = -Ei;
-  const double tr = ar * pr - ai * pi_, ti = ar * pi_ + ai * pr;
-  const double Qr = (tr * Dr + ti * Di) * inD, Qi = (ti * Dr - tr * Di) * inD;
+  const double tr = fma(ar, pr, -(ai * pi_)), ti = fma(ar, pi_, ai * pr);
+  const double Qr = fma(tr, Dr, ti * Di) * inD, Qi = fma(ti, Dr, -(tr * Di)) * inD;
   // B*v0 = (m * inv_s2) * Q * v0
   const double msr = mr * s.inv_s2[j], msi = mi * s.inv_s2[j];
-  const double Br = msr * Qr - msi * Qi, Bi = msr * Qi + msi * Qr;
+  const double Br = fma(msr, Qr, -(msi * Qi)), Bi = fma(msr, Qi, msi * Qr);
   // log(D/(2d)) : modulus from |D|^2/(4|d|^2) with |d|^2 = |z| = h ; argument from D*conj(d)
   const double lr = 0.5 * fm::log_ratio(nD, 4.0 * h);
-  const double li = fm::atan2_(Di * dr - Dr * di, Dr * dr + Di * di);
+  const double li = fm::atan2_(fma(Di, dr, -(Dr * di)), fma(Dr, dr, Di * di));
   FactorTerms f;
   f.Ar = s.c[j] * (mr * T - 2.0 * lr);
   f.Ai = s.c[j] * (mi * T - 2.0 * li);
