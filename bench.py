@@ -310,13 +310,14 @@ def run_b200_arm(args, wl):
         achieved = per_gpu * fpp / 1e12
         kernel_ms = total_ms / args.steps
         bytes_alg = P * (13 * 8 + nK * nT * 8)
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        traffic, ncu = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_summary.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
+                ncu = json.load(open(tpath)).get(args.workload)
+                traffic = ncu.get("dram_bytes_per_launch") if ncu else None
             except Exception:      # noqa: BLE001
-                traffic = None
+                traffic, ncu = None, None
         hbm_peak = None
         ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(ppath):
@@ -340,7 +341,18 @@ def run_b200_arm(args, wl):
                          "peak_source": "dhj_fp64_peak DFMA-chain probe on this GPU (MEASURED_PEAKS.json has no FP64 "
                                         "figure)", "nominal_peak": NOMINAL_FP64_TFLOPS,
                          "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
-                         "flop_per_price": fpp, "kernel": "k_price", "kernel_ms": kernel_ms,
+                         "flop_per_price": fpp, "kernel": "k_price_batch" if nK <= 8 else "k_price_dense",
+                         "kernel_ms": kernel_ms,
+                         "note": "achieved = prices/s x SURVEY §8d contract FLOP/price (the reference's formulas: one "
+                                 "sincos per strike and k). The kernel contracts strikes by rotation recurrences and "
+                                 "executes fewer flops, so frac can exceed 1; see `executed` and DESIGN.md §5",
+                         "executed": None if not ncu else {
+                             "flop_per_price": ncu["executed_flop_per_price"],
+                             "tflops": per_gpu * ncu["executed_flop_per_price"] / 1e12,
+                             "frac_of_peak": per_gpu * ncu["executed_flop_per_price"] / 1e12 / fp64_peak,
+                             "ncu_fp64_pipe_active_pct": ncu["fp64_pipe_active_pct"],
+                             "ncu_issue_active_pct": ncu["issue_active_pct"],
+                             "source": "profiles/ncu_summary.json (ncu --set full of the same kernel)"},
                          "hbm": {"achieved_gbs": bytes_alg / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "note": "compute-bound path: algorithmic bytes / kernel time, for information"}},
             "clocks": clocks.summary(),
