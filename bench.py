@@ -247,6 +247,7 @@ def run_b200_arm(args, wl):
     d_out = torch.empty((P, nT, nK), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
     gathered = torch.zeros((world, 2), dtype=torch.float64, device=dev)
+    mine = torch.tensor([[0.0, float(n_prices)]], dtype=torch.float64, device=dev)   # (checksum, count) of this rank
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_kernel():
@@ -274,8 +275,8 @@ def run_b200_arm(args, wl):
             e0.record()
             step_kernel()
             if world > 1:                      # gather the per-rank results checksum over NVLink
-                mine = torch.stack([d_out.sum(), d_out.new_tensor(float(n_prices))])
-                dist.all_gather_into_tensor(gathered, mine.view(1, 2))
+                mine[0, 0].copy_(d_out.sum())             # device-side, no host synchronisation
+                dist.all_gather_into_tensor(gathered, mine)
             e1.record()
         barrier()
     launches = ctx.launch_count - launches0
