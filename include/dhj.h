@@ -132,6 +132,24 @@ DHJ_API int dhj_truncation_range(dhj_ctx* ctx, const double* params, int64_t P, 
 DHJ_API int dhj_chi_psi(dhj_ctx* ctx, const int32_t* k, int32_t n, double c, double d, double a, double b,
                 double* out_chi, double* out_psi);
 
+/* ---- batched host optimiser (many simultaneous calibrations) --------------------------------- */
+/* Lock-step batch of independent, unconstrained L-BFGS-B instances: the algorithm scipy runs for
+ * minimize(method='L-BFGS-B') without bounds (lbfgs_calibrator.py:259-269; m = 10, More'-Thuente line search
+ * with at most maxls = 20 trials, stop on max|g| <= pgtol or (f_old - f) <= ftol * max(|f_old|,|f|,1), iteration
+ * and evaluation limits), restated so that one `ask` / one GPU launch (dhj_loss_fd) / one `tell` advances
+ * every calibration at once.  Host-only code.  status[i]: 0 converged (pgtol), 1 converged (ftol),
+ * 2 iteration limit, 3 evaluation limit, 4 abnormal (line search failed). */
+typedef struct dhj_lbfgs dhj_lbfgs;
+DHJ_API int dhj_lbfgs_create(int64_t n_states, int32_t dim, int32_t m, int32_t maxiter, int32_t maxfun, int32_t maxls,
+                             double ftol, double pgtol, const double* x0, dhj_lbfgs** out);
+DHJ_API int dhj_lbfgs_destroy(dhj_lbfgs* opt);
+/* states that wait for an evaluation: idx[n_active] (state numbers) and x[n_active][dim]; n_active = 0: all done */
+DHJ_API int dhj_lbfgs_ask(dhj_lbfgs* opt, int64_t* n_active, int64_t* idx, double* x);
+/* f[n_active], g[n_active][dim] in the order of the last ask */
+DHJ_API int dhj_lbfgs_tell(dhj_lbfgs* opt, int64_t n_active, const double* f, const double* g);
+/* any output may be NULL: x[n][dim], f[n], nit[n], nfev[n], status[n] */
+DHJ_API int dhj_lbfgs_result(const dhj_lbfgs* opt, double* x, double* f, int32_t* nit, int32_t* nfev, int32_t* status);
+
 /* ---- measurement ---------------------------------------------------------------------------- */
 /* Runs a register-resident FP64 FMA-chain kernel on every SM and reports the sustained DFMA rate
  * (2 flop per FMA) — the denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 figure). */

@@ -24,6 +24,7 @@ EXPORTS = (
     "dhj_price_list", "dhj_price_grid", "dhj_price_grid_dev",
     "dhj_market_create", "dhj_market_destroy", "dhj_loss_batch", "dhj_loss_fd", "dhj_market_prices",
     "dhj_cf", "dhj_truncation_range", "dhj_chi_psi", "dhj_fp64_peak",
+    "dhj_lbfgs_create", "dhj_lbfgs_destroy", "dhj_lbfgs_ask", "dhj_lbfgs_tell", "dhj_lbfgs_result",
 )
 
 
@@ -81,6 +82,13 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
                                              _F64]
         lib.dhj_chi_psi.argtypes = [_c_vp, _I32, _c_i32, _c_f64, _c_f64, _c_f64, _c_f64, _F64, _F64]
         lib.dhj_fp64_peak.argtypes = [_c_vp, _c_i32, ctypes.POINTER(_c_f64), ctypes.POINTER(_c_f64)]
+        _I64 = ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+        lib.dhj_lbfgs_create.argtypes = [_c_i64, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_f64, _c_f64, _F64,
+                                         ctypes.POINTER(_c_vp)]
+        lib.dhj_lbfgs_destroy.argtypes = [_c_vp]
+        lib.dhj_lbfgs_ask.argtypes = [_c_vp, ctypes.POINTER(_c_i64), _I64, _F64]
+        lib.dhj_lbfgs_tell.argtypes = [_c_vp, _c_i64, _F64, _F64]
+        lib.dhj_lbfgs_result.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]
         for name in EXPORTS:
             if name not in ("dhj_last_error",):
                 getattr(lib, name).restype = ctypes.c_int
@@ -314,6 +322,76 @@ class Market:
         with c._lock:
             c._check(c._lib.dhj_market_prices(c._h, self._h, x, pidx, B, out), "dhj_market_prices")
         return out
+
+
+class BatchLBFGS:
+    """Lock-step batch of unconstrained L-BFGS-B instances (dhj_lbfgs_*): host-only, no device needed.
+
+        opt = BatchLBFGS(x0)                      # x0[n, dim]
+        while True:
+            idx, x = opt.ask()
+            if idx.size == 0: break
+            f, g = evaluate(x, idx)               # e.g. Market.loss_fd(x, market_index=...)
+            opt.tell(f, g)
+        x, f, nit, nfev, status = opt.result()
+    """
+
+    MESSAGES = ("CONVERGENCE: NORM OF PROJECTED GRADIENT <= PGTOL",
+                "CONVERGENCE: RELATIVE REDUCTION OF F <= FACTR*EPSMCH",
+                "STOP: TOTAL NO. OF ITERATIONS REACHED LIMIT",
+                "STOP: TOTAL NO. OF F,G EVALUATIONS EXCEEDS LIMIT",
+                "ABNORMAL: ")
+
+    def __init__(self, x0, maxiter=300, ftol=1e-9, gtol=1e-6, m=10, maxfun=15000, maxls=20):
+        self._lib = load_library()
+        x0 = _f64(x0)
+        if x0.ndim != 2:
+            raise ValueError("x0 must be [n_states, dim]")
+        self.n, self.dim = x0.shape
+        self._h = _c_vp()
+        rc = self._lib.dhj_lbfgs_create(self.n, self.dim, int(m), int(maxiter), int(maxfun), int(maxls), float(ftol),
+                                        float(gtol), x0, ctypes.byref(self._h))
+        if rc != 0:
+            raise NativeError(f"dhj_lbfgs_create failed ({rc})")
+        self._idx = np.empty(self.n, dtype=np.int64)
+        self._x = np.empty((self.n, self.dim))
+        self._n_active = 0
+
+    def ask(self):
+        n = _c_i64()
+        rc = self._lib.dhj_lbfgs_ask(self._h, ctypes.byref(n), self._idx, self._x)
+        if rc != 0:
+            raise NativeError(f"dhj_lbfgs_ask failed ({rc})")
+        self._n_active = n.value
+        return self._idx[:n.value].copy(), self._x[:n.value].copy()
+
+    def tell(self, f, g):
+        f, g = _f64(f).reshape(-1), _f64(g).reshape(-1, self.dim)
+        if f.size != self._n_active or g.shape[0] != self._n_active:
+            raise ValueError("tell() needs one f and one g per point of the last ask()")
+        rc = self._lib.dhj_lbfgs_tell(self._h, self._n_active, f, g)
+        if rc != 0:
+            raise NativeError(f"dhj_lbfgs_tell failed ({rc})")
+
+    def result(self):
+        x, f = np.empty((self.n, self.dim)), np.empty(self.n)
+        nit, nfev, status = (np.empty(self.n, dtype=np.int32) for _ in range(3))
+        rc = self._lib.dhj_lbfgs_result(self._h, x.ctypes.data, f.ctypes.data, nit.ctypes.data, nfev.ctypes.data,
+                                        status.ctypes.data)
+        if rc != 0:
+            raise NativeError(f"dhj_lbfgs_result failed ({rc})")
+        return x, f, nit, nfev, status
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dhj_lbfgs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _default_ctx: Context | None = None

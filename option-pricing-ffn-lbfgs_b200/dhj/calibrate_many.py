@@ -1,0 +1,157 @@
+"""Many independent calibrations at once (BASELINE config C5): every calibration x start is one state of the
+batched host optimiser (`BatchLBFGS`, csrc/dhj_lbfgs.cpp), and every optimiser round is ONE launch of the fused
+loss / forward-difference kernel over all states that still run (`Market.loss_fd` with a per-state market).
+
+Semantics per market are those of `DoubleHestonJumpCalibrator.calibrate(maxiter, multi_start)`
+(/root/reference/src/calibration/lbfgs_calibrator.py:236-336): starts `i % 3` -> literature / perturbed /
+ATM-implied initial guess (the perturbed guess draws 13 uniforms from the global NumPy RNG, market by market,
+in start order), L-BFGS-B with ftol 1e-9, gtol 1e-6, the strictly lowest final loss wins (first start on ties).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from ._native import BatchLBFGS, Context, default_context
+
+PARAM_NAMES = ('v1_0', 'kappa1', 'theta1', 'sigma1', 'rho1', 'v2_0', 'kappa2', 'theta2', 'sigma2', 'rho2',
+               'lambda_j', 'mu_j', 'sigma_j')
+_LITERATURE = np.array([0.04, 2.5, 0.04, 0.3, -0.7, 0.04, 0.5, 0.04, 0.2, -0.5, 0.15, -0.04, 0.08])
+
+
+def inverse_transform(p: np.ndarray) -> np.ndarray:
+    """Model parameters -> unconstrained x (lbfgs_calibrator.py:89-109), rows of 13."""
+    p = np.asarray(p, dtype=np.float64)
+    x = np.log(np.where(np.arange(13) == 11, 1.0, p))
+    x[..., 4] = np.arctanh(np.clip(p[..., 4], -0.999, 0.999))
+    x[..., 9] = np.arctanh(np.clip(p[..., 9], -0.999, 0.999))
+    x[..., 11] = p[..., 11]
+    return x
+
+
+def transform(x: np.ndarray) -> np.ndarray:
+    """Unconstrained x -> model parameters (lbfgs_calibrator.py:62-87)."""
+    x = np.asarray(x, dtype=np.float64)
+    p = np.exp(x)
+    p[..., 4] = np.tanh(x[..., 4])
+    p[..., 9] = np.tanh(x[..., 9])
+    p[..., 11] = x[..., 11]
+    return p
+
+
+def initial_guesses(spots, strikes, maturities, prices, multi_start=3) -> np.ndarray:
+    """x0[n_markets, multi_start, 13] with the reference's three guess types (lbfgs_calibrator.py:179-234)."""
+    spots = np.asarray(spots, dtype=np.float64).reshape(-1)
+    n = spots.size
+    strikes = np.broadcast_to(np.asarray(strikes, dtype=np.float64), (n, np.asarray(maturities).size))
+    prices = np.asarray(prices, dtype=np.float64).reshape(n, -1)
+    maturities = np.asarray(maturities, dtype=np.float64).reshape(-1)
+    out = np.empty((n, multi_start, 13))
+    for i in range(n):
+        for s in range(multi_start):
+            kind = s % 3
+            if kind == 0:
+                p = _LITERATURE.copy()
+            elif kind == 1:
+                p = np.empty(13)
+                for j in range(13):                                       # dict order of the reference (:202-206)
+                    w = 0.15 if j in (4, 9, 11) else 0.20
+                    p[j] = _LITERATURE[j] * (1 + np.random.uniform(-w, w))
+                p[4] = np.clip(p[4], -0.95, -0.3)
+                p[9] = np.clip(p[9], -0.95, -0.3)
+            else:
+                ratio = strikes[i] / spots[i]
+                atm = (ratio > 0.95) & (ratio < 1.05)
+                if atm.any():
+                    iv = (np.mean(prices[i][atm]) / spots[i]) / np.sqrt(np.mean(maturities[atm]))
+                    iv = max(0.01, min(0.1, iv))
+                else:
+                    iv = 0.04
+                p = np.array([iv, 2.0, iv, 0.4, -0.6, iv, 0.7, iv, 0.25, -0.4, 0.12, -0.03, 0.07])
+            out[i, s] = inverse_transform(p)
+    return out
+
+
+def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, maxiter=300, multi_start=3,
+                   x0=None, ctx: Context | None = None, return_all_starts=False):
+    """Calibrate n markets simultaneously.
+
+    spots[n]; strikes[M] or [n, M]; maturities[M]; is_call[M]; prices[n, M]; optional x0[n, multi_start, 13].
+    Returns a dict of arrays: x[n,13], parameters[n,13], final_loss[n], iterations[n], success[n], status[n],
+    best_start[n], model_prices[n,M], rounds (launches), seconds; with `return_all_starts` also the per-start
+    x / loss / nit / status.
+    """
+    t0 = time.time()
+    ctx = ctx or default_context()
+    spots = np.ascontiguousarray(np.asarray(spots, dtype=np.float64).reshape(-1))
+    n = spots.size
+    maturities = np.asarray(maturities, dtype=np.float64).reshape(-1)
+    prices = np.asarray(prices, dtype=np.float64).reshape(n, maturities.size)
+    if x0 is None:
+        x0 = initial_guesses(spots, strikes, maturities, prices, multi_start)
+    x0 = np.asarray(x0, dtype=np.float64).reshape(n * multi_start, 13)
+    market = ctx.market(spots, risk_free_rate, strikes, maturities, is_call, prices)
+    state_market = np.repeat(np.arange(n, dtype=np.int32), multi_start)
+    opt = BatchLBFGS(x0, maxiter=maxiter, ftol=1e-9, gtol=1e-6)
+    rounds = 0
+    while True:
+        idx, x = opt.ask()
+        if idx.size == 0:
+            break
+        f, g = market.loss_fd(x, 1e-8, market_index=state_market[idx])
+        opt.tell(f, g)
+        rounds += 1
+    xs, fs, nit, nfev, status = opt.result()
+    opt.close()
+    fs2, xs2 = fs.reshape(n, multi_start), xs.reshape(n, multi_start, 13)
+    # strictly lowest loss wins, first start on ties; NaN never wins (lbfgs_calibrator.py:271)
+    key = np.where(np.isnan(fs2), np.inf, fs2)
+    best = np.argmin(key, axis=1)
+    rows = np.arange(n)
+    bx = xs2[rows, best]
+    model = market.prices(bx, market_index=np.arange(n, dtype=np.int32)) if n else np.empty((0, maturities.size))
+    market.close()
+    out = {
+        'x': bx, 'parameters': transform(bx), 'final_loss': fs2[rows, best],
+        'iterations': nit.reshape(n, multi_start)[rows, best],
+        'status': status.reshape(n, multi_start)[rows, best],
+        'success': status.reshape(n, multi_start)[rows, best] <= 1,
+        'best_start': best, 'model_prices': model, 'rounds': rounds, 'evaluations': int(nfev.sum()) * 14,
+        'seconds': time.time() - t0,
+    }
+    if return_all_starts:
+        out.update({'all_x': xs2, 'all_loss': fs2, 'all_nit': nit.reshape(n, multi_start),
+                    'all_status': status.reshape(n, multi_start)})
+    return out
+
+
+def calibrate_many_sharded(spots, risk_free_rate, strikes, maturities, is_call, prices, group=None, device=None,
+                           **kwargs):
+    """One process per GPU: each rank calibrates its contiguous block of markets, results are all-gathered
+    (NCCL over NVLink on the GPU box).  Initial guesses are drawn for ALL markets on every rank (same global
+    RNG stream everywhere) so the result does not depend on the number of ranks."""
+    from .shard import gather_rows, shard_bounds, _dist
+    dist = _dist()
+    world = dist.get_world_size(group) if dist else 1
+    rank = dist.get_rank(group) if dist else 0
+    spots = np.asarray(spots, dtype=np.float64).reshape(-1)
+    n = spots.size
+    maturities = np.asarray(maturities, dtype=np.float64).reshape(-1)
+    prices = np.asarray(prices, dtype=np.float64).reshape(n, maturities.size)
+    strikes = np.asarray(strikes, dtype=np.float64)
+    ms = kwargs.get('multi_start', 3)
+    x0 = kwargs.pop('x0', None)
+    if x0 is None:
+        x0 = initial_guesses(spots, strikes, maturities, prices, ms)
+    lo, hi = shard_bounds(n, world, rank)
+    k_local = strikes if strikes.size == maturities.size else strikes.reshape(n, -1)[lo:hi]
+    local = calibrate_many(spots[lo:hi], risk_free_rate, k_local, maturities, is_call, prices[lo:hi],
+                           x0=np.asarray(x0).reshape(n, ms, 13)[lo:hi], **kwargs)
+    out = {}
+    for key in ('x', 'parameters', 'final_loss', 'iterations', 'status', 'success', 'best_start', 'model_prices'):
+        arr = np.asarray(local[key])
+        out[key] = gather_rows(arr.astype(np.float64) if arr.dtype == bool else arr, n, group, device)
+    out['success'] = out['success'].astype(bool)
+    out['rounds'], out['seconds'] = local['rounds'], local['seconds']
+    return out
