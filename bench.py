@@ -54,6 +54,11 @@ WORKLOADS = {
     "c3": dict(P=1024, strikes=list(np.linspace(80.0, 120.0, 200)), maturities=list(np.linspace(0.25, 2.0, 20)),
                N=256, r=0.03,
                name="C3: dense surface 200K x 20T, N=256, 1024 parameter sets per launch"),
+    # C4: the 100 M-set dataset, STRONG scaling: the sets are divided over the ranks, parameters generated on the device
+    "c4": dict(P=100_000_000, strikes=[90.0, 95.0, 100.0, 105.0, 110.0], maturities=[0.25, 0.5, 1.0], N=128, r=0.03,
+               strong=True, device_params=True,
+               name="C4: synthetic_generator dataset, 100M parameter sets x 15 options (K = K_rel*spot/100), N=128, "
+                    "sharded by parameter set"),
 }
 
 
@@ -234,16 +239,33 @@ def run_b200_arm(args, wl):
     ctx = dhj.Context(local)
 
     P, N, r = wl["P"], wl["N"], wl["r"]
+    if wl.get("strong"):
+        P = -(-P // world)                                   # this rank's block of the fixed total
     strikes, mats = np.array(wl["strikes"]), np.array(wl["maturities"])
     nK, nT = strikes.size, mats.size
     n_prices = P * nK * nT
 
     # synthetic inputs: pinned host copy (for the e2e arm) and HBM-resident copy (kernel arm)
-    h_params = torch.from_numpy(gen_params(P, 20260101 + rank)).pin_memory()
-    h_s0 = torch.full((1,), 100.0, dtype=torch.float64).pin_memory()
-    h_out = torch.empty((P, nT, nK), dtype=torch.float64).pin_memory()
-    d_params = h_params.to(dev)
-    d_s0 = h_s0.to(dev)
+    if wl.get("device_params"):
+        # too large to stage through NumPy comfortably: uniform draws on the device (torch's Philox), same ranges
+        gen = torch.Generator(device=dev); gen.manual_seed(7 + rank)
+        lo_t = torch.tensor(PARAM_RANGES[:, 0], device=dev); hi_t = torch.tensor(PARAM_RANGES[:, 1], device=dev)
+        d_big = torch.rand((P, 13), dtype=torch.float64, device=dev, generator=gen) * (hi_t - lo_t) + lo_t
+        P_e2e = 1 << 20
+        h_params = d_big[:P_e2e].cpu().pin_memory()
+    else:
+        d_big, P_e2e = None, P
+        h_params = torch.from_numpy(gen_params(P, 20260101 + rank)).pin_memory()
+    scaled = bool(wl.get("device_params"))                  # C4: per-set spot, strikes scale with it
+    if scaled:
+        d_s0_big = 100.0 * torch.exp(0.05 * torch.randn((P,), dtype=torch.float64, device=dev, generator=gen))
+        h_s0 = d_s0_big[:P_e2e].cpu().pin_memory()
+    else:
+        d_s0_big = None
+        h_s0 = torch.full((1,), 100.0, dtype=torch.float64).pin_memory()
+    h_out = torch.empty((P_e2e, nT, nK), dtype=torch.float64).pin_memory()
+    d_params = d_big if d_big is not None else h_params.to(dev)
+    d_s0 = d_s0_big if d_s0_big is not None else h_s0.to(dev)
     d_out = torch.empty((P, nT, nK), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
     gathered = torch.zeros((world, 2), dtype=torch.float64, device=dev)
@@ -251,8 +273,8 @@ def run_b200_arm(args, wl):
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_kernel():
-        ctx.price_grid_dev(d_params.data_ptr(), P, d_s0.data_ptr(), 0, strikes, mats, r, 0.0, N, 10.0, False, True,
-                           d_out.data_ptr(), stream)
+        ctx.price_grid_dev(d_params.data_ptr(), P, d_s0.data_ptr(), 1 if scaled else 0, strikes, mats, r, 0.0, N, 10.0,
+                           scaled, True, d_out.data_ptr(), stream)
 
     def barrier():
         if world > 1:
@@ -291,19 +313,19 @@ def run_b200_arm(args, wl):
     # ---- end-to-end arm: host buffers through the C-ABI -------------------------------------------
     np_params, np_s0, np_out = h_params.numpy(), h_s0.numpy(), h_out.numpy()
     for _ in range(max(1, min(args.warmup, 3))):
-        ctx.price_grid(np_params, np_s0, strikes, mats, r, 0.0, N, 10.0, False, True, out=np_out)
+        ctx.price_grid(np_params, np_s0, strikes, mats, r, 0.0, N, 10.0, scaled, True, out=np_out)
     e2e_steps = max(3, min(args.steps, 10))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.price_grid(np_params, np_s0, strikes, mats, r, 0.0, N, 10.0, False, True, out=np_out)
+        ctx.price_grid(np_params, np_s0, strikes, mats, r, 0.0, N, 10.0, scaled, True, out=np_out)
         _ = float(np_out[0, 0, 0])             # the result is on the host when the call returns
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_prices * e2e_steps / float(e2e_s.item())
-    e2e_match = bool(np.array_equal(np_out, d_out.cpu().numpy()))
+    e2e_value = world * P_e2e * nK * nT * e2e_steps / float(e2e_s.item())
+    e2e_match = bool(np.array_equal(np_out, d_out[:P_e2e].cpu().numpy()))
 
     if rank == 0:
         per_gpu = value / world
@@ -325,15 +347,16 @@ def run_b200_arm(args, wl):
             hbm_peak = json.load(open(ppath)).get("hbm_gbs")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": kernel_ms, "higher_is_better": True,
+            "scaling": "strong" if wl.get("strong") else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "sets_per_gpu": P, "options_per_set": nK * nT, "N": N,
                        "l2": "256 MiB buffer written between timed steps (untimed); inputs+outputs = "
                              f"{bytes_alg / 2**20:.0f} MiB per step",
                        "sharding": "by parameter set, one batch per rank, NCCL all_gather of checksums per step"
                                    if world > 1 else "single GPU"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P * 13 * 8 + 8),
-                    "d2h_bytes_per_step": int(n_prices * 8), "steps": e2e_steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P_e2e * 13 * 8 + (P_e2e * 8 if scaled else 8)),
+                    "d2h_bytes_per_step": int(P_e2e * nK * nT * 8), "steps": e2e_steps, "sets_per_step": P_e2e,
                     "api": "dhj.Context.price_grid -> dhj_price_grid (pinned host in/out)",
                     "bit_identical_to_kernel_arm": e2e_match},
             "gpu_launches": int(launches),

@@ -233,13 +233,21 @@ class DoubleHestonJumpCalibrator:
         return minimize(fun=fun_and_grad, x0=x0, jac=True, method='L-BFGS-B',
                         options={'maxiter': maxiter, 'ftol': 1e-9, 'gtol': 1e-6})
 
-    def calibrate(self, maxiter: int = 300, multi_start: int = 3) -> CalibrationResult:
-        """Calibrate to the market prices with `multi_start` L-BFGS-B runs; the best (lowest loss) wins."""
+    def calibrate(self, maxiter: int = 300, multi_start: int = 3, *, x0=None) -> CalibrationResult:
+        """Calibrate to the market prices with `multi_start` L-BFGS-B runs; the best (lowest loss) wins.
+
+        `x0` (keyword-only extension, not in the reference): optional unconstrained starting points
+        [multi_start, 13] replacing the built-in guesses — the warm-start hook for an FFN predictor
+        (docs/METHODOLOGY.md:112-134 of the reference describes that pipeline; its code is not in the repo).
+        """
         start_time = time.time()
         market = self._device_market()
 
         # initial points in start order: keeps the reference's global-RNG consumption (:252-256)
-        x0s = [self.get_initial_guess(guess_type=i % 3) for i in range(multi_start)]
+        if x0 is None:
+            x0s = [self.get_initial_guess(guess_type=i % 3) for i in range(multi_start)]
+        else:
+            x0s = [np.array(v, dtype=np.float64) for v in np.asarray(x0, dtype=np.float64).reshape(multi_start, 13)]
         results = [None] * multi_start
         finished_at = [None] * multi_start
         counters = [[0, np.inf] for _ in range(multi_start)]          # per-start n_calls, best_loss

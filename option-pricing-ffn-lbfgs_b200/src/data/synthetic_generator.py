@@ -73,9 +73,11 @@ def _draw_inputs(n):
     return names, params, spots, noise
 
 
-def generate_synthetic_arrays(n_samples, ctx=None):
+def generate_synthetic_arrays(n_samples, ctx=None, save_path=None):
     """Flat-array form of the generator: dict of params[n,13], spots[n], strikes[n,15], maturities[15],
-    model_prices[n,15], market_prices[n,15], losses[n] (same values as the object form)."""
+    model_prices[n,15], market_prices[n,15], losses[n] (same values as the object form).  With `save_path` the
+    arrays are also written as one .npz — the on-disk form for datasets too large for a pickle of Python
+    objects."""
     ctx = ctx or default_context()
     names, params, spots, noise = _draw_inputs(n_samples)
     model = ctx.price_grid(params, spots, STRIKES.astype(np.float64), MATURITIES, RISK_FREE,
@@ -83,9 +85,12 @@ def generate_synthetic_arrays(n_samples, ctx=None):
     market = model + noise * model                                              # (:141-142)
     rel = (model - market) / market
     strikes = np.tile(STRIKES[None, :] * spots[:, None] / 100.0, (1, MATURITIES.size))
-    return {'param_names': names, 'params': params, 'spots': spots, 'strikes': strikes,
+    data = {'param_names': names, 'params': params, 'spots': spots, 'strikes': strikes,
             'maturities': np.repeat(MATURITIES, STRIKES.size), 'model_prices': model,
             'market_prices': market, 'losses': np.mean(rel ** 2, axis=1)}
+    if save_path is not None:
+        np.savez(save_path, **{k: np.asarray(v) for k, v in data.items()})
+    return data
 
 
 def generate_synthetic_calibrations(n_samples: int = 500,

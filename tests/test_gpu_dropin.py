@@ -194,3 +194,48 @@ def test_calibrate_many(mods, golden):
     assert (ratio < 3.0).all() and (ratio > 1 / 3.0).all()
     # the launch count is that of the slowest state, not the sum over states
     assert res['rounds'] <= 21 * 301
+
+
+def test_puts_parity_and_jump_limit(mods):
+    """The checks the reference's docs promise but its suite does not run (docs/METHODOLOGY.md:150-156):
+    put-call parity across the grid, the lambda -> 0 limit, and price bounds."""
+    dh, _, _ = mods
+    import dhj
+    ctx = dhj.default_context()
+    p = np.array([TS[k] for k in ("v01", "kappa1", "theta1", "sigma1", "rho1", "v02", "kappa2", "theta2", "sigma2",
+                                  "rho2", "lambda_j", "mu_j", "sigma_j")])
+    K = np.tile([80.0, 90.0, 100.0, 110.0, 120.0], 3); T = np.repeat([0.25, 1.0, 2.0], 5)
+    r = 0.05
+    call = ctx.price_list(p, 100.0, K, T, np.ones(15), r)[0]
+    put = ctx.price_list(p, 100.0, K, T, np.zeros(15), r)[0]
+    parity = call - put - (100.0 - K * np.exp(-r * T))
+    assert np.abs(parity).max() < 1e-3                       # the demo's tolerance is 0.01 (double_heston.py:299)
+    assert (call > np.maximum(100.0 - K * np.exp(-r * T), 0) - 1e-9).all() and (call < 100.0).all()
+    # lambda -> 0: continuous approach to the no-jump price (SURVEY Appendix B: 13.480108655594977 at lambda = 0)
+    no_jump = p.copy(); no_jump[10:] = 0.0
+    base = ctx.price_list(no_jump, 100.0, [100.0], [1.0], [1], r)[0, 0]
+    assert rel_err(base, 13.480108655594977) <= 1e-10
+    prev = None
+    for lam in (1e-2, 1e-4, 1e-8):
+        q = p.copy(); q[10] = lam
+        v = ctx.price_list(q, 100.0, [100.0], [1.0], [1], r)[0, 0]
+        assert abs(v - base) < 2 * lam * 5.0
+        assert prev is None or abs(v - base) <= abs(prev - base)
+        prev = v
+
+
+def test_warm_start_hook_and_flat_arrays(mods, golden, tmp_path):
+    _, cal, gen = mods
+    gi = golden("initial_guess.npz")
+    c = c1_calibrator(cal, gi)
+    x_true = c.inverse_transform_params(dict(zip(c.param_names, [0.04, 2.0, 0.04, 0.3, -0.5, 0.04, 1.5, 0.04, 0.2, -0.3,
+                                                                 0.1, 0.0, 0.1])))
+    res = c.calibrate(maxiter=50, multi_start=1, x0=x_true[None, :] + 0.01)
+    assert res.final_loss < 1e-5
+    np.random.seed(42)
+    path = str(tmp_path / "flat.npz")
+    data = gen.generate_synthetic_arrays(20, save_path=path)
+    g = golden("generator_seed42.npz")
+    assert rel_err(data["model_prices"], g["model_prices"]).max() <= 1e-10
+    again = np.load(path)
+    assert np.array_equal(again["market_prices"], data["market_prices"]) and again["params"].shape == (20, 13)
