@@ -189,7 +189,9 @@ int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_s
   const long long items = a.P * (long long)v.n_slices;
   if (max_slice <= kBatchMaxStrikes) {
     const long long batches = (items + kBatchItems - 1) / kBatchItems;
-    const long long cap = (long long)ctx->sm_count * ctx->batch_blocks_per_sm;
+    // one block per batch: the hardware block scheduler balances the SMs dynamically (a persistent grid with a
+    // static batch -> block map measured ~3 % slower: the slowest SM sets the time)
+    const long long cap = 2147483647LL;
     // DHJ_DEBUG_EXTRA_SMEM (bytes): developer knob that pads the launch with unused dynamic shared memory to
     // lower the resident block count (occupancy experiments, profiles/README.md); never set in production
     static const size_t extra = [] {
@@ -200,7 +202,7 @@ int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_s
     }();
     k_price_batch<<<(int)std::max<long long>(1, std::min(batches, cap)), kBatchThreads, extra, st>>>(v, a);
   } else {
-    const long long cap = (long long)ctx->sm_count * ctx->dense_blocks_per_sm;
+    const long long cap = 2147483647LL;
     k_price_dense<<<(int)std::max<long long>(1, std::min(items, cap)), kBatchThreads, 0, st>>>(v, a);
   }
   DHJ_CUDA(ctx, cudaGetLastError());
@@ -580,7 +582,7 @@ static int run_loss(dhj_ctx* ctx, const dhj_market* mk, const double* x, const i
     const long long resident = (long long)ctx->sm_count * ctx->loss_blocks_per_sm;
     a.units_per_batch = (int)std::max<long long>(1, std::min<long long>(upb_max, n_units / resident));
     const long long batches = (n_units + a.units_per_batch - 1) / a.units_per_batch;
-    k_loss_batch<<<(int)std::max<long long>(1, std::min(batches, resident)), kBatchThreads, 0, ctx->stream>>>(v, a);
+    k_loss_batch<<<(int)std::max<long long>(1, std::min(batches, 2147483647LL)), kBatchThreads, 0, ctx->stream>>>(v, a);
     DHJ_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
   } else {
