@@ -23,10 +23,13 @@ namespace dhj {
 
 constexpr int kBatchThreads = 128;
 constexpr int kBatchWarps = kBatchThreads / 32;
-constexpr int kBatchItems = 32;
+#ifndef DHJ_BATCH_ITEMS
+#define DHJ_BATCH_ITEMS 32
+#endif
+constexpr int kBatchItems = DHJ_BATCH_ITEMS;
 constexpr int kBatchMaxStrikes = 8;
 #ifndef DHJ_BATCH_MINB
-#define DHJ_BATCH_MINB 4
+#define DHJ_BATCH_MINB 7
 #endif
 
 struct ItemRec {

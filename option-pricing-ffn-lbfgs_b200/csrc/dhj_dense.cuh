@@ -15,6 +15,9 @@
 namespace dhj {
 
 constexpr int kDenseChunk = 256;
+#ifndef DHJ_DENSE_MINB
+#define DHJ_DENSE_MINB 6
+#endif
 
 struct DenseSmem {
   SetConsts set;

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
 }
 
 // Many strikes per slice: one block per item, lane per strike (dhj_dense.cuh).
-__global__ void __launch_bounds__(kBatchThreads, 4) k_price_dense(SliceView v, PriceArgs a) {
+__global__ void __launch_bounds__(kBatchThreads, DHJ_DENSE_MINB) k_price_dense(SliceView v, PriceArgs a) {
   __shared__ DenseSmem sm;
   const int tid = threadIdx.x;
   const long long n_items = a.P * (long long)v.n_slices;
@@ -174,7 +174,7 @@ struct LossBatchArgs {
   unsigned int* counters;    // fd: [C]
 };
 
-__global__ void __launch_bounds__(kBatchThreads, 4) k_loss_batch(SliceView v, LossBatchArgs a) {
+__global__ void __launch_bounds__(kBatchThreads, 6) k_loss_batch(SliceView v, LossBatchArgs a) {
   __shared__ BatchSmem sm;
   __shared__ double s_price[kBatchItems][kBatchMaxStrikes];
   __shared__ double s_feller[kBatchItems];
