@@ -50,10 +50,16 @@ struct BatchSmem {
   PassConsts extra_pass;           // pass constants of a binding strike
   double extra_cth, extra_sth;     // and its rotation step
   CoefStage stage[kBatchWarps];
+  fm::LogEntry ltab[64];           // fm::log_tab's table (per-lane index: shared memory, not the constant bank)
   double partial[kBatchItems][kBatchWarps][kBatchMaxStrikes];
 };
 
 struct PriceArgs;                  // dhj_kernels.cuh
+
+// every block copies the log table into its shared memory once
+__device__ __forceinline__ void load_log_table(fm::LogEntry* dst, int tid) {
+  if (tid < 64) dst[tid] = fm::kLogTable[tid];
+}
 
 // u_1 = (1*pi)/(b-a), the rotation step's frequency (same correction step as make_kterm)
 __device__ __forceinline__ double u_one(const PassConsts& p) {
@@ -93,7 +99,8 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
 // 8-term segments, reduced over the 4 segments by two shuffles and accumulated into the warp's partial.
 __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConsts& pc, const double* __restrict__ cth,
                                               const double* __restrict__ sth, unsigned mask, int n_cos, int tid,
-                                              CoefStage& st, double* __restrict__ warp_partial) {
+                                              CoefStage& st, const fm::LogEntry* __restrict__ ltab,
+                                              double* __restrict__ warp_partial) {
   constexpr int kSeg = 8, kNumSeg = 32 / kSeg;
   const int lane = tid & 31;
 #pragma unroll 1
@@ -101,7 +108,7 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
     const int k = k0 + tid;
     KCoef c;
     c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
-    if (k < n_cos) c = make_kcoef(make_kterm(it.set, pc, k), pc, k);
+    if (k < n_cos) c = make_kcoef(make_kterm(it.set, pc, k, ltab), pc, k);
     __syncwarp();
     st.P[lane] = c.P; st.Q[lane] = c.Q; st.R[lane] = c.R;
     // A1, A2 feed calls, A3 puts (uniform per pass); g0 is non-zero only in the lane that holds k = 0

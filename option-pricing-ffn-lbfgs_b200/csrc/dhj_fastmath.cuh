@@ -238,6 +238,36 @@ DHJ_FM double log_ratio(double a, double b) {
 }
 DHJ_FM double log_(double x) { return log_ratio(x, 1.0); }
 
+// ---- table-driven log ------------------------------------------------------------------------------
+// log(w) = e ln2 - log(r_i) + log1p(f r_i - 1) for w = 2^e f, f in [1,2), i = top 6 mantissa bits, r_i ~ 1/f:
+// |f r_i - 1| <= 2^-7, so a degree-7 Taylor polynomial of log1p is exact to 2e-18.  No division (log_ratio spends
+// 8 FP64 instructions on one) and no exponent alignment: 12 FP64 + ~7 integer instructions.  Absolute error
+// <= 2e-16 max(1, |log w|).  The table (1 KB) is read with a per-lane index, so the kernels keep it in shared
+// memory.  w must be a positive normal number; NaN / inf give NaN.
+struct LogEntry { double r, l; };
+#if defined(__CUDACC__)
+__device__ const LogEntry kLogTable[64] = {
+#else
+static const LogEntry kLogTable[64] = {
+#endif
+#include "dhj_logtable.inc"
+};
+
+DHJ_FM double log_tab(double w, const LogEntry* __restrict__ tab) {
+  const int hi = hi32(w);
+  const int e = ((hi >> 20) & 0x7ff) - 1023;
+  const LogEntry t = tab[(hi >> 14) & 63];
+  const double f = from_hilo((hi & 0x000fffff) | 0x3ff00000, lo32(w));
+  const double ep = fma(f, t.r, -1.0);
+  double q = 1.0 / 7.0;
+  q = fma(q, ep, -1.0 / 6.0); q = fma(q, ep, 0.2); q = fma(q, ep, -0.25); q = fma(q, ep, 1.0 / 3.0);
+  q = fma(q, ep, -0.5);
+  const double l1p = fma(ep * ep, q, ep);
+  const double ef = (double)e;
+  const double res = fma(ef, kS.Ln2HiFull, t.l) + fma(ef, kS.Ln2LoFull, l1p);
+  return res + (w - w);                     // NaN or inf in -> NaN out (the bit surgery above would launder them)
+}
+
 // ---- atan2 -----------------------------------------------------------------------------------------
 // atan(t) = t - t z P(z), z = t^2, |t| <= tan(pi/8)  (fdlibm aT[0..10], designed for |t| < 7/16)
 DHJ_CONSTANT double kAt[11] = {3.33333333333329318027e-01, -1.99999999998764832476e-01, 1.42857142725034663711e-01,

@@ -168,7 +168,8 @@ DHJ_HD PassConsts make_pass_consts(const SetConsts& s, double a, double b, doubl
 // reference/glibc operation order; g itself is never formed.
 struct FactorTerms { double Ar, Ai, Bvr, Bvi; };
 
-DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) {
+DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
+                                 const fm::LogEntry* __restrict__ ltab) {
   const double kap = s.kappa[j];
   const double bi = -(s.rs[j] * u);                 // Im beta
   const double s2u = s.s2[j] * u;
@@ -209,7 +210,8 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) 
   const double msr = mr * s.inv_s2[j], msi = mi * s.inv_s2[j];
   const double Br = fma(msr, Qr, -(msi * Qi)), Bi = fma(msr, Qi, msi * Qr);
   // log(D/(2d)) : modulus from |D|^2/(4|d|^2) with |d|^2 = |z| = h ; argument from D*conj(d)
-  const double lr = 0.5 * fm::log_ratio(nD, 4.0 * h);
+  // (log of the reciprocal ratio through the table-driven log: 4|z| / |D|^2 is one multiply away)
+  const double lr = -0.5 * fm::log_tab((4.0 * h) * inD, ltab);
   const double li = fm::atan2_(fma(Di, dr, -(Dr * di)), fma(Dr, dr, Di * di));
   FactorTerms f;
   f.Ar = s.c[j] * (mr * T - 2.0 * lr);
@@ -222,12 +224,17 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T) 
 // exponent X of cf_heston * cf_jump = exp(X) at frequency u  (double_heston.py:82-96):
 //   X = ((A0 + A1) + A2) + B1 v01 + B2 v02  +  lamT (exp(i u mu - hsj2 u^2) - 1),  A0 = i (drift u) T
 // The two factors run through ONE rolled copy of heston_factor (instruction-cache footprint).
-DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, double* xr_out, double* xi_out) {
+DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, const fm::LogEntry* __restrict__ ltab,
+                        double* xr_out, double* xi_out) {
   double aR = 0.0, aI = (s.drift * u) * T;
   double b1r = 0.0, b1i = 0.0, b2r = 0.0, b2i = 0.0;
+#ifdef DHJ_UNROLL_FACTORS
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
   for (int j = 0; j < 2; ++j) {
-    const FactorTerms f = heston_factor(s, j, u, T);
+    const FactorTerms f = heston_factor(s, j, u, T, ltab);
     aR += f.Ar; aI += f.Ai;
     if (j == 0) { b1r = f.Bvr; b1i = f.Bvi; } else { b2r = f.Bvr; b2i = f.Bvi; }
   }
@@ -252,7 +259,7 @@ struct KTerm {
   double t3;     // (u * sin(u (b-a))) * e^b
 };
 
-DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k) {
+DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k, const fm::LogEntry* __restrict__ ltab) {
   KTerm t;
   // u = (k*pi)/(b-a): quotient from the precomputed reciprocal plus one correction step
   const double kpi = (double)k * kPi;
@@ -260,7 +267,7 @@ DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k) {
   const double u = fma(fma(-p.w, q0, kpi), p.rw, q0);
   t.u = u;
   double xr, xi;
-  cf_exponent(s, u, p.T, p.lamT, &xr, &xi);
+  cf_exponent(s, u, p.T, p.lamT, ltab, &xr, &xi);
   // Re( cf_heston * cf_jump * e^{-i u a} ) with the three exponentials merged
   // (the k = 0 weight 1/2 of double_heston.py:188 is folded in here: scaling by 2^-1 commutes exactly)
   t.G = (fm::exp_(xr) * fm::cos_(xi - u * p.a)) * ((k == 0) ? 0.5 : 1.0);

@@ -28,6 +28,7 @@ def fmlib():
     lib.fm_exp.argtypes = [D, ctypes.c_int, D]
     lib.fm_log_ratio.argtypes = [D, D, ctypes.c_int, D]
     lib.fm_atan2.argtypes = [D, D, ctypes.c_int, D]
+    lib.fm_log_tab.argtypes = [D, ctypes.c_int, D]
     lib.fm_div.argtypes = [D, D, ctypes.c_int, D]
     lib.fm_rcp.argtypes = [D, ctypes.c_int, D]
     lib.fm_sqrt.argtypes = [D, ctypes.c_int, D, D]
@@ -105,6 +106,21 @@ def test_log_ratio(fmlib):
     assert ulp_err(o2, [mp.log(mp.mpf(float(x))) for x in a2]).max() <= 2.0
     assert np.isnan(_one(fmlib, "log_ratio", np.nan, 1.0)) and np.isnan(_one(fmlib, "log_ratio", 1.0, np.nan))
     assert _one(fmlib, "log_ratio", 3.0, 3.0) == 0.0
+
+
+def test_log_tab(fmlib):
+    rng = np.random.default_rng(6)
+    w = np.ascontiguousarray(np.concatenate([np.exp(rng.uniform(-40, 40, 4000)), rng.uniform(0.2, 2.0, 4000),
+                                             1.0 + rng.uniform(-1e-3, 1e-3, 500), [1.0, 0.5, 2.0, 1.0 - 2 ** -53]]))
+    o = np.empty_like(w)
+    fmlib.fm_log_tab(w, w.size, o)
+    exact = [mp.log(mp.mpf(float(v))) for v in w]
+    err = np.array([float(abs(mp.mpf(float(g)) - e)) for g, e in zip(o, exact)])
+    assert (err / np.maximum(1.0, np.abs(o))).max() <= 2.3e-16, (err / np.maximum(1.0, np.abs(o))).max()
+    assert abs(o[-4]) <= 5e-18                 # log(1): the table entry and the polynomial cancel to rounding
+    bad = np.array([np.nan, np.inf]); ob = np.empty(2)
+    fmlib.fm_log_tab(bad, 2, ob)
+    assert np.isnan(ob).all()
 
 
 def test_atan2(fmlib):
