@@ -41,36 +41,41 @@ def transform(x: np.ndarray) -> np.ndarray:
 
 
 def initial_guesses(spots, strikes, maturities, prices, multi_start=3) -> np.ndarray:
-    """x0[n_markets, multi_start, 13] with the reference's three guess types (lbfgs_calibrator.py:179-234)."""
+    """x0[n_markets, multi_start, 13] with the reference's three guess types (lbfgs_calibrator.py:179-234).
+
+    Vectorised over markets.  The perturbed guesses (start index % 3 == 1) consume the global NumPy RNG exactly
+    as sequential `calibrate` calls would: market-major, then start, then the 13 parameters in dict order, each
+    `value * (1 + uniform(-w, w))` with w = 0.15 for rho1, rho2, mu_j and 0.20 otherwise (:202-206)."""
     spots = np.asarray(spots, dtype=np.float64).reshape(-1)
     n = spots.size
-    strikes = np.broadcast_to(np.asarray(strikes, dtype=np.float64), (n, np.asarray(maturities).size))
-    prices = np.asarray(prices, dtype=np.float64).reshape(n, -1)
     maturities = np.asarray(maturities, dtype=np.float64).reshape(-1)
-    out = np.empty((n, multi_start, 13))
-    for i in range(n):
-        for s in range(multi_start):
-            kind = s % 3
-            if kind == 0:
-                p = _LITERATURE.copy()
-            elif kind == 1:
-                p = np.empty(13)
-                for j in range(13):                                       # dict order of the reference (:202-206)
-                    w = 0.15 if j in (4, 9, 11) else 0.20
-                    p[j] = _LITERATURE[j] * (1 + np.random.uniform(-w, w))
-                p[4] = np.clip(p[4], -0.95, -0.3)
-                p[9] = np.clip(p[9], -0.95, -0.3)
-            else:
-                ratio = strikes[i] / spots[i]
-                atm = (ratio > 0.95) & (ratio < 1.05)
-                if atm.any():
-                    iv = (np.mean(prices[i][atm]) / spots[i]) / np.sqrt(np.mean(maturities[atm]))
-                    iv = max(0.01, min(0.1, iv))
-                else:
-                    iv = 0.04
-                p = np.array([iv, 2.0, iv, 0.4, -0.6, iv, 0.7, iv, 0.25, -0.4, 0.12, -0.03, 0.07])
-            out[i, s] = inverse_transform(p)
-    return out
+    strikes = np.broadcast_to(np.asarray(strikes, dtype=np.float64), (n, maturities.size))
+    prices = np.asarray(prices, dtype=np.float64).reshape(n, -1)
+    p = np.empty((n, multi_start, 13))
+    kinds = np.arange(multi_start) % 3
+    p[:, kinds == 0] = _LITERATURE
+    n1 = int((kinds == 1).sum())
+    if n1:
+        w = np.where(np.isin(np.arange(13), (4, 9, 11)), 0.15, 0.20)
+        draws = np.random.uniform(-w, w, size=(n, n1, 13))                 # same stream order as scalar draws
+        pert = _LITERATURE * (1 + draws)
+        pert[..., 4] = np.clip(pert[..., 4], -0.95, -0.3)
+        pert[..., 9] = np.clip(pert[..., 9], -0.95, -0.3)
+        p[:, kinds == 1] = pert
+    if (kinds == 2).any():
+        ratio = strikes / spots[:, None]
+        atm = (ratio > 0.95) & (ratio < 1.05)
+        cnt = atm.sum(axis=1)
+        with np.errstate(all="ignore"):
+            avg_price = np.where(atm, prices, 0.0).sum(axis=1) / cnt
+            avg_mat = np.where(atm, maturities[None, :], 0.0).sum(axis=1) / cnt
+            iv = np.clip((avg_price / spots) / np.sqrt(avg_mat), 0.01, 0.1)
+        iv = np.where(cnt > 0, iv, 0.04)
+        g2 = np.empty((n, 13))
+        g2[:] = [0.0, 2.0, 0.0, 0.4, -0.6, 0.0, 0.7, 0.0, 0.25, -0.4, 0.12, -0.03, 0.07]
+        g2[:, [0, 2, 5, 7]] = iv[:, None]
+        p[:, kinds == 2] = g2[:, None, :]
+    return inverse_transform(p)
 
 
 def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, maxiter=300, multi_start=3,

@@ -259,3 +259,29 @@ def test_many_strikes_and_slices(ctx):
     T2 = np.linspace(0.1, 2.0, 40); K2 = np.full(40, 100.0)
     got2 = ctx.price_list(params, 100.0, K2, T2, np.ones(40), 0.03)
     assert rel_err(got2, O.price_batch(params, 100.0, K2, T2, np.ones(40), 0.03)).max() <= PRICE_RTOL
+
+
+def test_full_size_c2_properties(ctx):
+    """BASELINE config C2 at FULL size (1 048 576 parameter sets x 15 options, N = 128) through size-independent
+    properties: run-to-run determinism, agreement of the grid and list entry points, put-call parity on every
+    price, monotonicity in strike and maturity, and the oracle on a scattered sub-sample."""
+    rng = np.random.default_rng(20260101)
+    P = 1 << 20
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(P, 13))
+    Ks, Ts, r = O.GENERATOR_STRIKES_REL, O.GENERATOR_MATURITIES, 0.03
+    calls = ctx.price_grid(params, 100.0, Ks, Ts, r)
+    again = ctx.price_grid(params, 100.0, Ks, Ts, r)
+    assert np.array_equal(calls, again)                                   # deterministic, launch to launch
+    assert np.isfinite(calls).all() and (calls > 0).all()
+    puts = ctx.price_grid(params, 100.0, Ks, Ts, r, is_call=False)
+    parity = calls - puts - (100.0 - Ks[None, None, :] * np.exp(-r * Ts)[None, :, None])
+    print("C2 full size: max |put-call parity residual| = %.3e over %d prices" % (np.abs(parity).max(), calls.size))
+    assert np.abs(parity).max() < 1e-4                                    # COS truncation level of the reference (2e-10..1e-5)
+    assert (np.diff(calls, axis=2) < 0).all()                             # decreasing in strike
+    assert (np.diff(calls, axis=1) > 0).all()                             # increasing in maturity
+    sel = rng.choice(P, size=1500, replace=False)
+    K = np.tile(Ks, 3); T = np.repeat(Ts, 5)
+    want = O.price_batch(params[sel], 100.0, K, T, np.ones(15), r).reshape(-1, 3, 5)
+    assert rel_err(calls[sel], want).max() <= PRICE_RTOL
+    lst = ctx.price_list(params[sel], 100.0, K, T, np.ones(15), r).reshape(-1, 3, 5)
+    assert np.array_equal(lst, calls[sel])                                # list and grid entry points agree bit for bit

@@ -206,3 +206,24 @@ def test_sharded_pricing_gloo_world2():
     res = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(30) for p in procs]
     assert res == [(0, True, True, True), (1, True, True, True)]
+
+
+def test_vectorised_initial_guesses_match_calibrator(dropins):
+    """dhj.initial_guesses (many markets at once) = get_initial_guess market by market, same global RNG stream."""
+    _, cal, _ = dropins
+    from dhj.calibrate_many import initial_guesses
+    rng = np.random.default_rng(0)
+    n = 7
+    spots = rng.uniform(90, 110, n)
+    K = np.tile(np.array([90.0, 95, 100, 105, 110])[None, :] * spots[:, None] / 100, (1, 3))
+    K[3] *= 1.5                                             # a market without ATM options: implied_var falls back to 0.04
+    T = np.repeat([0.25, 0.5, 1.0], 5)
+    prices = rng.uniform(2, 15, (n, 15))
+    np.random.seed(5)
+    got = initial_guesses(spots, K, T, prices, 5)
+    np.random.seed(5)
+    for i in range(n):
+        c = cal.DoubleHestonJumpCalibrator(spots[i], 0.03, [
+            {"strike": K[i, j], "maturity": T[j], "price": prices[i, j], "option_type": "call"} for j in range(15)])
+        for s in range(5):
+            assert np.array_equal(got[i, s], c.get_initial_guess(s % 3)), (i, s)
