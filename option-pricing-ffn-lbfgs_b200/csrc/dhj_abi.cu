@@ -56,7 +56,6 @@ struct BookHost {
   std::vector<double> slice_T;
   std::vector<int> slice_off, pos;
   std::vector<unsigned char> call;
-  std::vector<double> strike;   // caller order; rows * M (or M when shared)
   void group(const double* maturity, const int32_t* is_call, int m) {
     M = m;
     slice_T.clear();
@@ -130,13 +129,11 @@ struct dhj_ctx {
   int device = 0;
   int sm_count = 0;
   int loss_blocks_per_sm = 1;
-  int batch_blocks_per_sm = 1;
-  int dense_blocks_per_sm = 1;
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   char err[512] = "";
   // cached option book for the pricing entry points
-  DevBuf d_book, d_tables;
+  DevBuf d_book;
   PinBuf h_book;
   std::vector<unsigned char> book_image;      // last uploaded packed image (+ strike table) for reuse
   Slot slots[kSlots];
@@ -386,12 +383,6 @@ int dhj_init(int device, dhj_ctx** out) {
     return DHJ_ERR_CUDA;
   }
   ctx->loss_blocks_per_sm = std::max(1, bps);
-  bps = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_price_batch, kBatchThreads, 0) != cudaSuccess) bps = 1;
-  ctx->batch_blocks_per_sm = std::max(1, bps);
-  bps = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_price_dense, kBatchThreads, 0) != cudaSuccess) bps = 1;
-  ctx->dense_blocks_per_sm = std::max(1, bps);
   *out = ctx;
   return DHJ_OK;
 }
@@ -406,7 +397,7 @@ int dhj_destroy(dhj_ctx* ctx) {
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  ctx->d_book.release(); ctx->d_tables.release(); ctx->h_book.release();
+  ctx->d_book.release(); ctx->h_book.release();
   ctx->d_x.release(); ctx->d_xv.release(); ctx->d_idx.release(); ctx->d_f.release(); ctx->d_fg.release();
   ctx->d_counters.release(); ctx->d_prices.release(); ctx->h_x.release(); ctx->h_res.release();
   ctx->d_peak.release();
