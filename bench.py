@@ -304,7 +304,11 @@ def run_b200_arm(args, wl):
     launches = ctx.launch_count - launches0
     ms_steps = [e0.elapsed_time(e1) for e0, e1 in ev]
     t_ms = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
+    per_rank_ms = [float(t_ms.item()) / args.steps]
     if world > 1:
+        all_ms = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(all_ms, t_ms)
+        per_rank_ms = [float(v) / args.steps for v in all_ms.tolist()]
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     total_ms = float(t_ms.item())
     value = world * n_prices * args.steps / (total_ms * 1e-3)
@@ -379,6 +383,7 @@ def run_b200_arm(args, wl):
                              "source": "profiles/ncu_summary.json (ncu --set full of the same kernel)"},
                          "hbm": {"achieved_gbs": bytes_alg / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                                  "note": "compute-bound path: algorithmic bytes / kernel time, for information"}},
+            "ms_per_step_per_rank": per_rank_ms,
             "clocks": clocks.summary(),
             "checksum": checksum,
         }
