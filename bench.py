@@ -268,8 +268,9 @@ def run_b200_arm(args, wl):
     d_s0 = d_s0_big if d_s0_big is not None else h_s0.to(dev)
     d_out = torch.empty((P, nT, nK), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
-    gathered = torch.zeros((world, 2), dtype=torch.float64, device=dev)
-    mine = torch.tensor([[0.0, float(n_prices)]], dtype=torch.float64, device=dev)   # (checksum, count) of this rank
+    # (checksum, count) of this rank, double-buffered so that a step's gather overlaps the next step's kernel
+    gathered = torch.zeros((2, world, 2), dtype=torch.float64, device=dev)
+    mine = torch.tensor([[[0.0, float(n_prices)]]] * 2, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_kernel():
@@ -292,14 +293,20 @@ def run_b200_arm(args, wl):
     launches0 = ctx.launch_count
     with ClockSampler(local) as clocks:
         barrier()
-        for e0, e1 in ev:
+        pending = None
+        for i, (e0, e1) in enumerate(ev):
             flush.zero_()                      # L2 flush, outside the timed events
             e0.record()
             step_kernel()
-            if world > 1:                      # gather the per-rank results checksum over NVLink
-                mine[0, 0].copy_(d_out.sum())             # device-side, no host synchronisation
-                dist.all_gather_into_tensor(gathered, mine)
+            if world > 1:                      # gather the per-rank results checksum over NVLink (NCCL), asynchronously:
+                buf = mine[i % 2]              # it runs on NCCL's stream while the next step's kernel computes
+                buf[0, 0].copy_(d_out.sum())   # device-side, no host synchronisation
+                if pending is not None:
+                    pending.wait()             # stream-level wait for the previous gather (its buffers are reused next)
+                pending = dist.all_gather_into_tensor(gathered[i % 2], buf, async_op=True)
             e1.record()
+        if pending is not None:
+            pending.wait()
         barrier()
     launches = ctx.launch_count - launches0
     ms_steps = [e0.elapsed_time(e1) for e0, e1 in ev]
