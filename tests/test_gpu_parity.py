@@ -285,3 +285,30 @@ def test_full_size_c2_properties(ctx):
     assert rel_err(calls[sel], want).max() <= PRICE_RTOL
     lst = ctx.price_list(params[sel], 100.0, K, T, np.ones(15), r).reshape(-1, 3, 5)
     assert np.array_equal(lst, calls[sel])                                # list and grid entry points agree bit for bit
+
+
+def test_host_path_chunking_and_memory_kinds(ctx):
+    """The host-buffer entry points stream chunks of <= 131 072 sets through two slots: results must not depend
+    on chunk boundaries, on per-set strikes / spots being present, or on the caller's memory being pinned."""
+    import torch
+    rng = np.random.default_rng(12)
+    P = 300_001                                                  # three chunks, the last one ragged
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(P, 13))
+    spots = rng.uniform(80, 120, size=P)
+    Ks, Ts = O.GENERATOR_STRIKES_REL, O.GENERATOR_MATURITIES
+    pageable = ctx.price_grid(params, spots, Ks, Ts, 0.03, scale_by_spot=True)
+    pin_p = torch.from_numpy(params).pin_memory(); pin_s = torch.from_numpy(spots).pin_memory()
+    pin_o = torch.empty((P, 3, 5), dtype=torch.float64).pin_memory()
+    pinned = ctx.price_grid(pin_p.numpy(), pin_s.numpy(), Ks, Ts, 0.03, scale_by_spot=True, out=pin_o.numpy())
+    assert np.array_equal(pageable, pinned)
+    # per-set strike rows through the list entry point give the same bits as the scaled grid
+    K = np.tile(Ks[None, :] * spots[:, None] / 100.0, (1, 3)); T = np.repeat(Ts, 5)
+    lst = ctx.price_list(params, spots, K, T, np.ones(15), 0.03)
+    assert np.array_equal(lst.reshape(P, 3, 5), pageable)
+    # rows around the chunk boundaries against single-set calls
+    for p in (0, 131071, 131072, 262143, 262144, P - 1):
+        one = ctx.price_grid(params[p], spots[p], Ks, Ts, 0.03, scale_by_spot=True)[0]
+        assert np.array_equal(one, pageable[p]), p
+    sel = rng.choice(P, size=300, replace=False)
+    want = O.price_batch(params[sel], spots[sel], K[sel], T, np.ones(15), 0.03).reshape(-1, 3, 5)
+    assert rel_err(pageable[sel], want).max() <= PRICE_RTOL
