@@ -20,6 +20,10 @@ def shard_bounds(n_items: int, world: int, rank: int) -> tuple[int, int]:
 
 
 def _dist():
+    # importing torch costs seconds: only look for a process group if somebody already imported it
+    import sys
+    if "torch" not in sys.modules:
+        return None
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized():
         return None
