@@ -182,8 +182,9 @@ DHJ_CONSTANT double kExpQ[10] = {0.50000000000000010212, 0.16666666666666674523,
                                  0.00002480152132015615238, 2.7557242364849317814e-6, 2.7620076799169896683e-7,
                                  2.5110039179932520501e-8};
 
-// core: p * 2^n with p in [0.70, 1.42]: n is added to p's exponent field (one integer add instead of building
-// 2^n and multiplying).  Valid while the result is a normal number: -708 < x < 709.7; callers guard the rest.
+// core: p * 2^n with p in [0.70, 1.42] and 2^n built in the exponent field.  The scaling is a multiplication, not
+// an integer add into p's exponent, so that a NaN p stays NaN whatever bits n carries.  Valid for
+// -708 < x < 709.08 (n in [-1022, 1023]); callers guard the rest.
 DHJ_FM double exp_core(double x) {
   const double t = fma(x, kS.Log2e, kRoundMagic);
   const int n = lo32(t);
@@ -195,13 +196,13 @@ DHJ_FM double exp_core(double x) {
   q = fma(q, r, kExpQ[4]); q = fma(q, r, kExpQ[3]); q = fma(q, r, kExpQ[2]); q = fma(q, r, kExpQ[1]);
   q = fma(q, r, kExpQ[0]);
   const double p = 1.0 + fma(r * r, q, r);
-  return from_hilo(hi32(p) + (n << 20), lo32(p));
+  return p * from_hilo((n + 1023) << 20, 0);
 }
 // full range
 DHJ_FM double exp_(double x) {
   double res = exp_core(x);
   res = (x < -708.0) ? 0.0 : res;          // results below the smallest normal are flushed to zero
-  res = (x > 709.7) ? (double)INFINITY : res;
+  res = (x > 709.08) ? (double)INFINITY : res;    // (e^709.08 = 8.9e307: the last 0.7 of the range overflows early)
   return res;
 }
 // for arguments known to be <= ~700 (decay factors): only the underflow side is guarded

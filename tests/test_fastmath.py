@@ -75,8 +75,8 @@ def _one(lib, name, *args):
 
 def test_exp(fmlib):
     rng = np.random.default_rng(2)
-    x = np.ascontiguousarray(np.concatenate([rng.uniform(-700, 700, 3000), rng.uniform(-40, 5, 3000),
-                                             rng.uniform(-1e-3, 1e-3, 500), [0.0, -745.0, -708.5, 709.69, 1.0, -1.0]]))
+    x = np.ascontiguousarray(np.concatenate([rng.uniform(-700, 709, 3000), rng.uniform(-40, 5, 3000),
+                                             rng.uniform(-1e-3, 1e-3, 500), [0.0, -745.0, -708.5, 709.0, 1.0, -1.0]]))
     o = np.empty_like(x)
     fmlib.fm_exp(x, x.size, o)
     e = ulp_err(o, [mp.exp(mp.mpf(float(v))) for v in x])

@@ -312,3 +312,32 @@ def test_host_path_chunking_and_memory_kinds(ctx):
     sel = rng.choice(P, size=300, replace=False)
     want = O.price_batch(params[sel], spots[sel], K[sel], T, np.ones(15), 0.03).reshape(-1, 3, 5)
     assert rel_err(pageable[sel], want).max() <= PRICE_RTOL
+
+
+def test_nan_and_inf_parameters_give_nan_everywhere(ctx):
+    """Every single parameter set to NaN / +inf / -inf in turn: the reference returns NaN (or, rarely, inf) silently;
+    nothing may come back as a plausible finite price, because the loss turns non-finite prices into the sentinel."""
+    base = np.array([0.04, 2.0, 0.04, 0.3, -0.5, 0.04, 1.5, 0.04, 0.2, -0.3, 0.1, -0.02, 0.1])
+    rows = []
+    for j in range(13):
+        for bad in (np.nan, np.inf, -np.inf):
+            p = base.copy(); p[j] = bad; rows.append(p)
+    rows = np.array(rows)
+    K = np.tile([90.0, 100.0, 110.0], 2); T = np.repeat([0.5, 1.0], 3)
+    got = ctx.price_list(rows, 100.0, K, T, [1, 1, 0, 0, 1, 1], 0.03)
+    with np.errstate(all="ignore"):
+        want = O.price_batch(rows, 100.0, K, T, [1, 1, 0, 0, 1, 1], 0.03)
+    # where the reference is non-finite so are we; a finite reference value (e.g. lambda = -inf is not one) must match
+    assert (~np.isfinite(got[~np.isfinite(want)])).all()
+    fin = np.isfinite(want)
+    assert np.isfinite(got[fin]).all() and rel_err(got[fin], want[fin]).max() <= 1e-9 if fin.any() else True
+    mk = ctx.market(100.0, 0.03, K, T, [1, 1, 0, 0, 1, 1], np.full(6, 5.0))
+    x = np.tile(O.inverse_transform_params(base), (6, 1))
+    x[0, 1] = np.nan; x[1, 3] = np.inf; x[2, 0] = -np.inf; x[3, 11] = np.nan; x[4, 4] = np.nan
+    loss = mk.loss_batch(x)
+    with np.errstate(all="ignore"):
+        ref = O.loss_batch(x, 100.0, 0.03, K, T, [1, 1, 0, 0, 1, 1], np.full(6, 5.0))
+    # (x = -inf for v1_0 means v1_0 = exp(-inf) = 0: a finite loss in the reference too)
+    assert np.array_equal(loss == 1e10, ref == 1e10) and (loss == 1e10).sum() == 4
+    assert np.abs(loss - ref).max() <= LOSS_ATOL
+    mk.close()
