@@ -276,7 +276,10 @@ DHJ_CONSTANT double kAt[11] = {3.33333333333329318027e-01, -1.999999999987648324
                                6.66107313738753120669e-02, -5.83357013379057348645e-02, 4.97687799461593236017e-02,
                                -3.65315727442169155270e-02, 1.62858201153657823623e-02};
 
-DHJ_FM double atan2_(double y, double x) {
+// ZERO_OK = false drops the atan2(+-0, +-0) special case (the hot path's argument D conj(d) is never zero; a zero
+// would give NaN): it costs a data-dependent branch pair per call otherwise.
+template <bool ZERO_OK>
+DHJ_FM double atan2_impl(double y, double x) {
   const double ax = fabs(x), ay = fabs(y);
   const bool steep = ay > ax;                       // NaN-safe: a NaN operand lands in mn or mx and propagates
   const double mx = steep ? ay : ax, mn = steep ? ax : ay;
@@ -293,9 +296,11 @@ DHJ_FM double atan2_(double y, double x) {
   r = hi ? (r + kS.PiO4Lo) + kS.PiO4 : r;     // atan(mn/mx) in [0, pi/4]
   r = steep ? kS.PiO2 - r : r;              // first quadrant angle
   r = (x < 0.0) ? kS.PiD - r : r;
-  r = (mx == 0.0) ? ((x < 0.0 || (x == 0.0 && signbit(x))) ? kS.PiD : 0.0) : r;   // atan2(+-0, +-0)
+  if (ZERO_OK) r = (mx == 0.0) ? ((x < 0.0 || (x == 0.0 && signbit(x))) ? kS.PiD : 0.0) : r;   // atan2(+-0, +-0)
   return copysign(r, y);
 }
+DHJ_FM double atan2_(double y, double x) { return atan2_impl<true>(y, x); }
+DHJ_FM double atan2_nz(double y, double x) { return atan2_impl<false>(y, x); }
 
 }  // namespace fm
 }  // namespace dhj
