@@ -109,6 +109,12 @@ def test_calibrate_c1(mods, golden):
     assert set(res.parameters) == set(c.param_names) and res.model_prices.shape == (15,)
     assert np.abs(res.model_prices - res.market_prices).max() / res.market_prices.max() < 0.01
     assert res.calibration_time <= wall and res.success in (True, False)
+    # the reference suite's parameter-range check (tests/test_suite.py:327-344)
+    boxes = {'v1_0': (0.001, 0.5), 'v2_0': (0.001, 0.5), 'kappa1': (0.1, 10.0), 'kappa2': (0.1, 10.0),
+             'theta1': (0.001, 0.5), 'theta2': (0.001, 0.5), 'sigma1': (0.01, 2.0), 'sigma2': (0.01, 2.0),
+             'rho1': (-1.0, 1.0), 'rho2': (-1.0, 1.0), 'lambda_j': (0.0, 5.0), 'sigma_j': (0.001, 1.0)}
+    for name, (lo, hi) in boxes.items():
+        assert lo <= res.parameters[name] <= hi, (name, res.parameters[name])
     # same starting points as the reference's run (global RNG order preserved)
     np.random.seed(0)
     assert np.array_equal(c.get_initial_guess(0), g["s0_x0"]) and np.array_equal(c.get_initial_guess(1), g["s1_x0"])
