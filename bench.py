@@ -227,6 +227,23 @@ def run_b200_arm(args, wl):
                         "per_core": v / cores,
                         "note": "oracle/cos_oracle.py price_scalar = the reference's per-option algorithm "
                                 "(src/models/double_heston.py:160-192), one process per host core"}
+        try:     # best-effort CPU line: the same arithmetic restated in C (oracle/cos_oracle.c), OpenMP over options
+            from oracle import cos_oracle as O
+            lib = O.c_library()
+            pc = gen_params(400 * cores, 777)
+            Kc = np.tile(np.array(wl["strikes"]), len(wl["maturities"]))
+            Tc = np.repeat(np.array(wl["maturities"]), len(wl["strikes"]))
+            O.c_price_batch(pc[:cores], 100.0, Kc, Tc, np.ones(Kc.size), wl["r"], 0.0, wl["N"])      # warm-up
+            t0c = time.perf_counter()
+            O.c_price_batch(pc, 100.0, Kc, Tc, np.ones(Kc.size), wl["r"], 0.0, wl["N"])
+            dtc = time.perf_counter() - t0c
+            cpu_baseline["c_port"] = {"value": pc.shape[0] * Kc.size / dtc, "unit": UNIT,
+                                      "threads": int(lib.oracle_threads()), "kind": "port",
+                                      "sample": f"{pc.shape[0]} parameter sets x {Kc.size} options, {dtc:.1f} s",
+                                      "note": "NOT the reference: oracle/cos_oracle.c, the reference's arithmetic in C99 "
+                                              "with OpenMP (a best-effort CPU implementation)"}
+        except Exception as e:      # noqa: BLE001
+            cpu_baseline["c_port"] = {"unavailable": repr(e)}
 
     import torch
     import torch.distributed as dist

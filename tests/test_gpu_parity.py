@@ -341,3 +341,20 @@ def test_nan_and_inf_parameters_give_nan_everywhere(ctx):
     assert np.array_equal(loss == 1e10, ref == 1e10) and (loss == 1e10).sum() == 4
     assert np.abs(loss - ref).max() <= LOSS_ATOL
     mk.close()
+
+
+def test_large_sample_vs_c_oracle(ctx):
+    """20 000 parameter sets x 15 options (300 000 prices) against the C restatement of the reference
+    (oracle/cos_oracle.c, pinned to the golden fixtures in tests/test_oracle_golden.py), puts and per-set spots included."""
+    rng = np.random.default_rng(31)
+    P = 20000
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(P, 13))
+    spots = rng.uniform(70, 140, size=P)
+    K = np.tile(O.GENERATOR_STRIKES_REL[None, :] * spots[:, None] / 100.0, (1, 3)); T = np.repeat(O.GENERATOR_MATURITIES, 5)
+    call = (np.arange(15) % 2 == 0)
+    got = ctx.price_list(params, spots, K, T, call, 0.03, 0.01)
+    want = O.c_price_batch(params, spots, K, T, call, 0.03, 0.01)
+    err = rel_err(got, want)
+    print("300k prices vs C oracle: max rel err %.3e, median %.3e, 99.9 %% below %.3e"
+          % (err.max(), np.median(err), np.quantile(err, 0.999)))
+    assert err.max() <= PRICE_RTOL

@@ -167,3 +167,47 @@ def test_oracle_generator_draws(golden):
     assert np.array_equal(market, g["market_prices"])
     # SURVEY §8c literal
     assert g["model_prices"][0, 0] == 12.426829764997922
+
+
+# ---- the C restatement (oracle/cos_oracle.c) -------------------------------------------------------------------
+def test_c_oracle_grid15_bit_identical(golden):
+    g = golden("prices_grid15.npz")
+    K = np.tile(g["k_rel"][None, :] * g["spots"][:, None] / 100.0, (1, 3))
+    T = np.repeat(g["maturities"], 5)
+    got, ab = O.c_price_batch(g["params"], g["spots"], K, T, np.ones(15), float(g["r"]), return_ab=True)
+    err = rel_err(got.reshape(150, 3, 5), g["prices"])
+    print("C oracle vs reference: max rel err %.3e, bit-identical %.1f %%" % (err.max(), 100 * (err == 0).mean()))
+    # not bit-identical: NumPy evaluates real exp / sin / cos / log with its own SIMD kernels, this file with glibc;
+    # the differences are single ulps amplified by the conditioning of the COS sum
+    assert err.max() <= 2e-13 and np.median(err) <= 2e-15
+    assert (err == 0).mean() >= 0.3
+    assert np.abs(ab.reshape(150, 3, 5, 2) - g["ab"]).max() <= 2e-15
+
+
+def test_c_oracle_edge_cases_and_dense(golden):
+    g = golden("edge_cases.npz")
+    for i in range(g["prices"].shape[0]):
+        S0, K, T, r, q, call, N = g["meta"][i]
+        got = O.c_price_batch(g["params"][i], S0, [K], [T], [call], r, q, int(N))[0, 0]
+        want = g["prices"][i]
+        if np.isnan(want):
+            assert np.isnan(got)
+        else:
+            scale = max(S0, K) * max(1.0, np.exp(g["ab"][i][1]))          # magnitude of the summands
+            assert abs(got - want) <= 1e-12 * abs(want) or abs(got - want) <= 4e-14 * scale, (i, got, want)
+    d = golden("dense_surface.npz")
+    for tag in ("main", "edge"):
+        Ks, Ts = d[f"{tag}_strikes"], d[f"{tag}_maturities"]
+        got = O.c_price_batch(d["params"], 100.0, np.tile(Ks, len(Ts)), np.repeat(Ts, len(Ks)), np.ones(Ks.size * Ts.size),
+                              float(d["r"]), N=256)
+        assert np.abs(got - d[f"{tag}_prices"].reshape(4, -1)).max() <= 1e-12
+
+
+def test_c_oracle_loss(golden):
+    g = golden("loss_cases.npz")
+    for tag in ("c1", "ragged"):
+        got = O.c_loss_batch(g[f"{tag}_x"], float(g[f"{tag}_spot"]), float(g[f"{tag}_r"]), g[f"{tag}_strike"],
+                             g[f"{tag}_maturity"], g[f"{tag}_is_call"], g[f"{tag}_market"])
+        want = g[f"{tag}_loss"]
+        assert np.array_equal(got == 1e10, want == 1e10)
+        assert np.all(np.abs(got - want) <= 1e-15 + 1e-13 * np.abs(want))
