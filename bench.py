@@ -230,7 +230,7 @@ def run_b200_arm(args, wl):
         try:     # best-effort CPU line: the same arithmetic restated in C (oracle/cos_oracle.c), OpenMP over options
             from oracle import cos_oracle as O
             lib = O.c_library()
-            pc = gen_params(400 * cores, 777)
+            pc = gen_params(2500 * cores, 777)
             Kc = np.tile(np.array(wl["strikes"]), len(wl["maturities"]))
             Tc = np.repeat(np.array(wl["maturities"]), len(wl["strikes"]))
             O.c_price_batch(pc[:cores], 100.0, Kc, Tc, np.ones(Kc.size), wl["r"], 0.0, wl["N"])      # warm-up
