@@ -164,8 +164,8 @@ DHJ_HD PassConsts make_pass_consts(const SetConsts& s, double a, double b, doubl
 //   m = beta - d ; pl = beta + d ; D = pl - m E          [1 - gE = D/pl ; 1 - g = 2d/pl]
 //   B = (m/sigma^2) (1-E)/(1-gE) = (m/sigma^2) (1-E) pl / D
 //   A = (kappa theta/sigma^2) (m T - 2 log((1-gE)/(1-g))) ,  (1-gE)/(1-g) = D/(2d)
-// (double_heston.py:64-71, 85-87).  beta^2, sigma^2 u (u+i) and the csqrt formula follow the
-// reference/glibc operation order; g itself is never formed.
+// (double_heston.py:64-71, 85-87).  The csqrt formula follows glibc's; products and sums are fused into FMAs
+// wherever possible (an FP64 instruction is the scarce resource); g itself is never formed.
 struct FactorTerms { double Ar, Ai, Bvr, Bvi; };
 
 DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
@@ -173,9 +173,9 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
   const double kap = s.kappa[j];
   const double bi = -(s.rs[j] * u);                 // Im beta
   const double s2u = s.s2[j] * u;
-  const double zr = (s.kk[j] - bi * bi) + s2u * u;  // Re(beta^2) + Re(sigma^2 u (u+i))
-  const double kb = kap * bi;
-  const double zi = (kb + kb) + s2u;
+  // z = beta^2 + sigma^2 u (u+i):  Re = kappa^2 - bi^2 + s2u u,  Im = 2 kappa bi + s2u   (fused: 3 FMAs)
+  const double zr = fma(s2u, u, fma(-bi, bi, s.kk[j]));
+  const double zi = fma(kap + kap, bi, s2u);
   // d = csqrt(z) as glibc does it: h = |z|, t = sqrt((h + |zr|)/2), other = zi/(2t); the roles of t and
   // `other` swap when Re z < 0.  (Re z >= kappa^2 > 0 for |rho| <= 1; the other case is kept for safety.)
   // (square roots as x * rsqrt(x): <= 1 ulp instead of correctly rounded, no zero special case; z = 0 needs
@@ -214,8 +214,8 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
   const double lr = -0.5 * fm::log_tab((4.0 * h) * inD, ltab);
   const double li = fm::atan2_nz(fma(Di, dr, -(Dr * di)), fma(Dr, dr, Di * di));
   FactorTerms f;
-  f.Ar = s.c[j] * (mr * T - 2.0 * lr);
-  f.Ai = s.c[j] * (mi * T - 2.0 * li);
+  f.Ar = s.c[j] * fma(mr, T, -2.0 * lr);
+  f.Ai = s.c[j] * fma(mi, T, -2.0 * li);
   f.Bvr = Br * s.v0[j];
   f.Bvi = Bi * s.v0[j];
   return f;
@@ -243,8 +243,8 @@ DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, con
   const double ej = fm::exp_neg(-(s.hsj2 * (u * u)));
   double sj, cj;
   fm::sincos_(u * s.mu, &sj, &cj);
-  xr += lamT * (ej * cj - 1.0);
-  xi += lamT * (ej * sj);
+  xr = fma(lamT, fma(ej, cj, -1.0), xr);
+  xi = fma(lamT, ej * sj, xi);
   *xr_out = xr; *xi_out = xi;
 }
 
@@ -270,7 +270,7 @@ DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k, const fm
   cf_exponent(s, u, p.T, p.lamT, ltab, &xr, &xi);
   // Re( cf_heston * cf_jump * e^{-i u a} ) with the three exponentials merged
   // (the k = 0 weight 1/2 of double_heston.py:188 is folded in here: scaling by 2^-1 commutes exactly)
-  t.G = (fm::exp_(xr) * fm::cos_(xi - u * p.a)) * ((k == 0) ? 0.5 : 1.0);
+  t.G = (fm::exp_(xr) * fm::cos_(fma(-u, p.a, xi))) * ((k == 0) ? 0.5 : 1.0);
   // sin / cos of fl(u (b-a)) = k pi + delta, |delta| <~ 1e-13: sin = (-1)^k delta, cos = (-1)^k exactly in
   // double (what libm returns for this argument), with delta from a two-term pi
   const double kf = (double)k;
