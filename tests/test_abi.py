@@ -72,3 +72,13 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.replace("oracle/", "").lower() or f == "__never__", os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/dhj.h must be consumable by a C compiler (cgo / JNI / ctypes-style bindings): no C++ in the boundary."""
+    src = tmp_path / "use_dhj.c"
+    src.write_text('#include "dhj.h"\nint main(void) { dhj_ctx* c = 0; (void)c; return dhj_abi_version() == DHJ_ABI_VERSION ? 0 : 1; }\n')
+    lib = os.path.join(PKG, "lib")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{os.path.join(ROOT, 'include')}", str(src),
+                    f"-L{lib}", "-ldhj", f"-Wl,-rpath,{lib}", "-o", str(tmp_path / "use_dhj")], check=True)
+    assert subprocess.run([str(tmp_path / "use_dhj")]).returncode == 0

@@ -358,3 +358,19 @@ def test_large_sample_vs_c_oracle(ctx):
     print("300k prices vs C oracle: max rel err %.3e, median %.3e, 99.9 %% below %.3e"
           % (err.max(), np.median(err), np.quantile(err, 0.999)))
     assert err.max() <= PRICE_RTOL
+
+
+def test_loss_many_slices(ctx):
+    """A market with 40 distinct maturities (more slices than one block batch holds): the loss goes through the
+    expand / price / reduce path and still matches the oracle."""
+    rng = np.random.default_rng(13)
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=13)
+    T = np.linspace(0.1, 2.0, 40); K = 100.0 + 10.0 * np.sin(np.arange(40)); call = (np.arange(40) % 2).astype(int)
+    market = O.price_batch(params, 100.0, K, T, call, 0.02)[0] * (1 + 0.01 * rng.standard_normal(40))
+    mk = ctx.market(100.0, 0.02, K, T, call, market)
+    x = O.inverse_transform_params(params)[None, :] + 0.05 * rng.standard_normal((4, 13))
+    f, g = mk.loss_fd(x)
+    want = O.loss_batch(x, 100.0, 0.02, K, T, call, market)
+    assert np.abs(f - want).max() <= LOSS_ATOL
+    assert np.array_equal(mk.loss_batch(x), f)
+    mk.close()
