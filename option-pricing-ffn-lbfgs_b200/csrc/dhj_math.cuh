@@ -340,18 +340,22 @@ DHJ_HD KCoef make_kcoef(const KTerm& t, const PassConsts& p, int k) {
   return c;
 }
 
-// sums over one segment: sum (P cos + Q sin) and sum R sin, starting from (c, s) = cos/sin(k0 theta)
+// sums over one segment: sum (P cos + Q sin) and sum R sin, starting from (c, s) = cos/sin(k0 theta).
+// cos/sin((k0+i) theta) advance by the three-term recurrence  t_{i+1} = 2 cos(theta) t_i - t_{i-1}  (one FMA per
+// sequence and step; the first step is a plane rotation by theta).  Its rounding error grows like i eps / sin(theta)
+// over the <= 32 steps of a segment (theta = pi (x-a)/(b-a) is >= pi * 0.1/(b-a) by the +-0.1 widening).
 DHJ_HD void segment_sums(const double* __restrict__ P, const double* __restrict__ Q, const double* __restrict__ R,
                          int seg, double c, double s, double cth, double sth, double* sum_pq, double* sum_r) {
-  double apq = 0.0, ar = 0.0;
+  double apq = fma(Q[0], s, P[0] * c), ar = R[0] * s;
+  double c1 = fma(c, cth, -(s * sth)), s1 = fma(s, cth, c * sth);     // (k0 + 1) theta
+  const double two_c = cth + cth;
 #pragma unroll 4
-  for (int i = 0; i < seg; ++i) {
-    apq = fma(P[i], c, apq);
-    apq = fma(Q[i], s, apq);
-    ar = fma(R[i], s, ar);
-    const double cn = fma(c, cth, -(s * sth));
-    s = fma(s, cth, c * sth);
-    c = cn;
+  for (int i = 1; i < seg; ++i) {
+    apq = fma(P[i], c1, apq);
+    apq = fma(Q[i], s1, apq);
+    ar = fma(R[i], s1, ar);
+    const double c2 = fma(two_c, c1, -c), s2 = fma(two_c, s1, -s);
+    c = c1; s = s1; c1 = c2; s1 = s2;
   }
   *sum_pq = apq; *sum_r = ar;
 }
