@@ -1,15 +1,16 @@
 // dhj_math.cuh — per-thread FP64 arithmetic of the COS pricer for the Double-Heston + Merton-jump model.
 //
-// Everything here is scalar code for ONE cosine index k of ONE (parameter set, maturity) pass; the
-// warp-level organisation (k = lane + 32*i, shuffles, strike loops) lives in dhj_engine.cuh.
+// Everything here is scalar code for ONE cosine index k of ONE (parameter set, maturity) pass, plus the
+// segment sums of the strike contraction; the thread / warp / block organisation lives in dhj_batch.cuh
+// (few strikes per maturity) and dhj_dense.cuh (many).
 // The functions restate the formulas of the reference in float64:
 //     truncation range   /root/reference/src/models/double_heston.py:100-139
 //     characteristic fn  /root/reference/src/models/double_heston.py:48-97
 //     payoff coefficients /root/reference/src/models/double_heston.py:141-158, 172-190
-// Where it is cheap the reference's own operation order is kept (so the arguments of sin/cos/exp
-// are the same doubles the reference feeds to libm); where it is expensive the algebra is
-// simplified (no g = (beta-d)/(beta+d); the three outer complex exponentials and e^{-iua} merged
-// into one exp and one cos).  DESIGN.md §4 lists every deviation and its measured effect.
+// The truncation range, u_k, the csqrt formula and the loss follow the reference's operation order;
+// elsewhere the algebra is simplified (no g = (beta-d)/(beta+d); the three outer complex exponentials
+// and e^{-iua} merged into one exp and one cos; strikes contracted by recurrences in k) and products and
+// sums are fused.  DESIGN.md §4 lists every deviation and its measured effect.
 //
 // The file compiles with nvcc (device) and with g++ (tests/host_emu: a test-only emulation that
 // lets the CPU test-suite check this arithmetic against the golden fixtures without a GPU; the
@@ -293,27 +294,6 @@ DHJ_HD StrikeConsts make_strike_consts(double K, double S0) {
   StrikeConsts c;
   c.K = K; c.x = fm::log_ratio(K, S0); c.ex = fm::exp_(c.x);
   return c;
-}
-
-// w_k * Re(phi_k e^{-i u_k a}) * V_k for one (k, strike)        double_heston.py:141-158, 176-188
-//   call: (c,d) = (x, b) ; put: (c,d) = (a, x).  `is_call` is uniform across the warp: a real branch.
-DHJ_HD double payoff_term(const KTerm& t, const PassConsts& p, const StrikeConsts& sc, double S0,
-                          bool is_call, int k) {
-  const double xa = sc.x - p.a;
-  double sn, cs;
-  fm::sincos_(t.u * xa, &sn, &cs);
-  const double cex = cs * sc.ex, usex = (t.u * sn) * sc.ex;
-  double V;
-  if (is_call) {
-    const double chi = t.inv1 * (((t.t1 - cex) + t.t3) - usex);
-    const double psi = (k == 0) ? (p.b - sc.x) : t.invu * (t.sb - sn);
-    V = p.tw * (S0 * chi - sc.K * psi);
-  } else {
-    const double chi = t.inv1 * ((cex - p.ea) + usex);
-    const double psi = (k == 0) ? xa : t.invu * sn;
-    V = p.tw * (sc.K * psi - S0 * chi);
-  }
-  return t.G * V;
 }
 
 // ---- rotation-based strike contraction -------------------------------------------------------------
