@@ -211,3 +211,22 @@ def test_c_oracle_loss(golden):
         want = g[f"{tag}_loss"]
         assert np.array_equal(got == 1e10, want == 1e10)
         assert np.all(np.abs(got - want) <= 1e-15 + 1e-13 * np.abs(want))
+
+
+def test_oracle_passes_the_reference_suites_own_checks():
+    """The only checks the reference's tests/test_suite.py holds for this path (sections 3.1-3.4, :194-262): ATM 1Y call
+    in (2, 15); prices decreasing in strike (>= 3 of 4 differences) and increasing in maturity; finite in 4 scenarios.
+    Applied to the oracle (the GPU path gets the same checks in tests/test_gpu_dropin.py)."""
+    p = np.array([0.04, 2.0, 0.04, 0.3, -0.5, 0.04, 1.5, 0.04, 0.2, -0.3, 0.1, 0.0, 0.1])
+    atm = O.price_scalar(p, 100.0, 100.0, 1.0, 0.05)
+    assert 2.0 < atm < 15.0 and abs(atm - 13.545233402249403) < 1e-12          # SURVEY §4: the suite prints 13.5452
+    by_strike = [O.price_scalar(p, 100.0, K, 1.0, 0.05) for K in (90, 95, 100, 105, 110)]
+    assert np.sum(np.diff(by_strike) < 0) >= 3
+    by_maturity = [O.price_scalar(p, 100.0, 100.0, T, 0.05) for T in (0.25, 0.5, 1.0)]
+    assert np.all(np.diff(by_maturity) > 0)
+    for S, K, T in ((100, 100, 0.25), (100, 100, 2.0), (100, 80, 1.0), (100, 120, 1.0)):
+        assert np.isfinite(O.price_scalar(p, S, K, T, 0.05))
+    # put-call parity of the demo (double_heston.py:292-299, tolerance 0.01)
+    d = np.array([0.04, 2.0, 0.04, 0.3, -0.5, 0.04, 1.5, 0.04, 0.2, -0.3, 0.5, -0.05, 0.10])
+    c, q = O.price_scalar(d, 100, 100, 1.0, 0.05, True), O.price_scalar(d, 100, 100, 1.0, 0.05, False)
+    assert abs((c - q) - (100 - 100 * np.exp(-0.05))) < 0.01
