@@ -53,3 +53,32 @@ if which in ("c2", "both"):
 if which in ("c3", "both"):
     ms, pps = bench(1024, np.linspace(80, 120, 200), np.linspace(0.25, 2.0, 20), 256, 5)
     print(f"[{tag}] C3 {ms:.2f} ms  {pps:.4g} prices/s")
+if which in ("loss", "all"):
+    import time
+    n = 10000
+    rng = np.random.default_rng(3)
+    params = rng.uniform(R[:, 0], R[:, 1], size=(n, 13))
+    spots = 100 * np.exp(0.05 * rng.standard_normal(n))
+    Ks = np.array([90.0, 95, 100, 105, 110]); Ts = np.array([0.25, 0.5, 1.0])
+    strikes = np.tile(Ks[None, :] * spots[:, None] / 100, (1, 3)); mats = np.repeat(Ts, 5)
+    market = ctx.price_grid(params, spots, Ks, Ts, 0.03, scale_by_spot=True).reshape(n, 15) * (1 + 0.02 * rng.standard_normal((n, 15)))
+    mk = ctx.market(spots, 0.03, strikes, mats, np.ones(15), market)
+    x = np.log(np.where(np.arange(13) == 11, 1.0, np.abs(params)))
+    x[:, 4] = np.arctanh(params[:, 4]); x[:, 9] = np.arctanh(params[:, 9]); x[:, 11] = params[:, 11]
+    x3 = np.repeat(x, 3, axis=0) + 0.05 * rng.standard_normal((3 * n, 13))
+    idx = np.repeat(np.arange(n, dtype=np.int32), 3)
+    mk.loss_fd(x3, 1e-8, idx)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        f, g = mk.loss_fd(x3, 1e-8, idx)
+    dt = (time.perf_counter() - t0) / 5
+    prices = 3 * n * 14 * 15
+    print(f"[{tag}] loss_fd: {3 * n} optimiser states x 14 stencil points x 15 options = {prices} prices in {dt * 1e3:.2f} ms "
+          f"(host call incl. copies) -> {prices / dt:.4g} prices/s, {3 * n / dt:.4g} f,g evaluations/s")
+    x1 = x3[:3]
+    mk1 = ctx.market(spots[0], 0.03, strikes[0], mats, np.ones(15), market[0])
+    mk1.loss_fd(x1)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        mk1.loss_fd(x1)
+    print(f"[{tag}] loss_fd latency, 3 states (one README calibration step): {(time.perf_counter() - t0) / 200 * 1e6:.1f} us per call")
