@@ -173,6 +173,19 @@ int fail(dhj_ctx* ctx, int code, const char* fmt, ...) {
                   "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);     \
   } while (0)
 
+// staging copies between the caller's pageable memory and the pinned slots: a single thread moves ~10 GB/s, less
+// than the kernel consumes per chunk, so large copies are split over a few host threads
+void host_copy(void* dst, const void* src, size_t bytes) {
+  constexpr size_t kPiece = (size_t)1 << 20;
+  if (bytes < 4 * kPiece) { memcpy(dst, src, bytes); return; }
+  const long long pieces = (long long)((bytes + kPiece - 1) / kPiece);
+#pragma omp parallel for schedule(static) num_threads(4)
+  for (long long i = 0; i < pieces; ++i) {
+    const size_t off = (size_t)i * kPiece;
+    memcpy((char*)dst + off, (const char*)src + off, std::min(kPiece, bytes - off));
+  }
+}
+
 bool is_pinned_host(const void* p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -259,7 +272,7 @@ int run_price_host(dhj_ctx* ctx, SliceView v, int max_slice, const double* param
     Slot& sl = ctx->slots[slot_i];
     // the slot's previous chunk must have left its buffers
     DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));
-    if (sl.pending) { memcpy(sl.user_out, sl.h_out.p, sl.out_bytes); sl.pending = false; }
+    if (sl.pending) { host_copy(sl.user_out, sl.h_out.p, sl.out_bytes); sl.pending = false; }
     const size_t pb = (size_t)n * kNumParams * sizeof(double);
     const size_t s0b = s0_stride ? (size_t)n * sizeof(double) : sizeof(double);
     const size_t kb = strike_stride ? (size_t)n * M * sizeof(double) : 0;
@@ -277,9 +290,9 @@ int run_price_host(dhj_ctx* ctx, SliceView v, int max_slice, const double* param
     } else {
       DHJ_CUDA(ctx, sl.h_in.reserve(pb + s0b + kb));
       unsigned char* hin = (unsigned char*)sl.h_in.p;
-      memcpy(hin, src_params, pb);
-      memcpy(hin + pb, src_s0, s0b);
-      if (kb) memcpy(hin + pb + s0b, src_strike, kb);
+      host_copy(hin, src_params, pb);
+      host_copy(hin + pb, src_s0, s0b);
+      if (kb) host_copy(hin + pb + s0b, src_strike, kb);
       DHJ_CUDA(ctx, cudaMemcpyAsync(din, hin, pb + s0b + kb, cudaMemcpyHostToDevice, sl.stream));
     }
     SliceView vv = v;
@@ -302,7 +315,7 @@ int run_price_host(dhj_ctx* ctx, SliceView v, int max_slice, const double* param
   for (int i = 0; i < kSlots; ++i) {
     Slot& sl = ctx->slots[i];
     DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));
-    if (sl.pending) { memcpy(sl.user_out, sl.h_out.p, sl.out_bytes); sl.pending = false; }
+    if (sl.pending) { host_copy(sl.user_out, sl.h_out.p, sl.out_bytes); sl.pending = false; }
   }
   return DHJ_OK;
 }
