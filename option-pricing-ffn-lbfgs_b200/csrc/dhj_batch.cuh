@@ -50,15 +50,15 @@ struct BatchSmem {
   PassConsts extra_pass;           // pass constants of a binding strike
   double extra_cth, extra_sth;     // and its rotation step
   CoefStage stage[kBatchWarps];
-  fm::LogEntry ltab[64];           // fm::log_tab's table (per-lane index: shared memory, not the constant bank)
+  fm::Tables ltab;                 // fm::log_tab / exp_tab tables (per-lane index: shared memory, not the constant bank)
   double partial[kBatchItems][kBatchWarps][kBatchMaxStrikes];
 };
 
 struct PriceArgs;                  // dhj_kernels.cuh
 
 // every block copies the log table into its shared memory once
-__device__ __forceinline__ void load_log_table(fm::LogEntry* dst, int tid) {
-  if (tid < 64) dst[tid] = fm::kLogTable[tid];
+__device__ __forceinline__ void load_log_table(fm::Tables* dst, int tid) {
+  if (tid < 64) { dst->log[tid] = fm::kTables.log[tid]; dst->exp2[tid] = fm::kTables.exp2[tid]; }
 }
 
 // u_1 = (1*pi)/(b-a), the rotation step's frequency (same correction step as make_kterm)
@@ -99,7 +99,7 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
 // 8-term segments, reduced over the 4 segments by two shuffles and accumulated into the warp's partial.
 __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConsts& pc, const double* __restrict__ cth,
                                               const double* __restrict__ sth, unsigned mask, int n_cos, int tid,
-                                              CoefStage& st, const fm::LogEntry* __restrict__ ltab,
+                                              CoefStage& st, const fm::Tables* __restrict__ ltab,
                                               double* __restrict__ warp_partial) {
   constexpr int kSeg = 8, kNumSeg = 32 / kSeg;
   const int lane = tid & 31;

@@ -25,7 +25,7 @@ struct DenseSmem {
   double a0, b0, S0, disc;
   double extra_cth, extra_sth;
   CoefStage stage[kBatchWarps];
-  fm::LogEntry ltab[64];
+  fm::Tables ltab;
   double K[kDenseChunk], x[kDenseChunk], ex[kDenseChunk], cth[kDenseChunk], sth[kDenseChunk];
   double partial[kBatchWarps][kDenseChunk];
   unsigned char call[kDenseChunk], bind[kDenseChunk];
@@ -44,7 +44,7 @@ __device__ __forceinline__ void dense_pass(DenseSmem& sm, const PassConsts& pc, 
     const int k = k0 + tid;
     KCoef c;
     c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
-    if (k < n_cos) c = make_kcoef(make_kterm(sm.set, pc, k, sm.ltab), pc, k);
+    if (k < n_cos) c = make_kcoef(make_kterm(sm.set, pc, k, &sm.ltab), pc, k);
     __syncwarp();
     st.P[lane] = c.P; st.Q[lane] = c.Q; st.R[lane] = c.R;
     const double A1 = warp_sum(c.a1), A2 = warp_sum(c.a2), A3 = warp_sum(c.P);

@@ -73,13 +73,12 @@ DHJ_FM double rsqrt_seed(double x) {
 #endif
 }
 
-// 1/x for normal x (two Newton steps from the seed; <= 1 ulp)
+// 1/x for normal x: one cubic step from the seed, r (1 + e + e^2) with e = 1 - x r, takes 20 bits to 60
+// (<= 1 ulp; `div` below repairs the last bit with the exact residual)
 DHJ_FM double rcp(double x) {
-  double r = rcp_seed(x);
-  double e = fma(-x, r, 1.0);
-  r = fma(fma(e, e, e), r, r);          // r (1 + e + e^2): cubic step, 20 -> 60 bits
-  e = fma(-x, r, 1.0);
-  return fma(e, r, r);
+  const double r = rcp_seed(x);
+  const double e = fma(-x, r, 1.0);
+  return fma(fma(e, e, e), r, r);
 }
 
 // a/b for normal operands and quotient (<= 1 ulp, nearly always correctly rounded)
@@ -90,13 +89,11 @@ DHJ_FM double div(double a, double b) {
 }
 
 // 1/sqrt(x) and sqrt(x) for normal x > 0 (sqrt(0) = 0 handled; <= 1 ulp)
+// one third-order step: y (1 + e/2 + 3 e^2/8) with e = 1 - x y^2, 20 bits -> 60
 DHJ_FM double rsqrt(double x) {
-  double y = rsqrt_seed(x);
-  const double hx = 0.5 * x;
-  double t = fma(-(hx * y), y, 0.5);
-  y = fma(y, t, y);
-  t = fma(-(hx * y), y, 0.5);
-  return fma(y, t, y);
+  const double y = rsqrt_seed(x);
+  const double e = fma(-(x * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
 }
 DHJ_FM void sqrt_rsqrt(double x, double* s_out, double* y_out) {
   const double y = rsqrt(x);
@@ -125,6 +122,9 @@ struct ScalarConsts {
   double PiO4Lo;
   double PiO2;
   double PiD;
+  double Log2e64;      // 64 / ln 2
+  double Ln2Hi64;      // (ln 2)/64, high 32 bits and the rest
+  double Ln2Lo64;
 };
 DHJ_CONSTANT ScalarConsts kS = {
   6.36619772367581382433e-01,
@@ -141,7 +141,10 @@ DHJ_CONSTANT ScalarConsts kS = {
   7.85398163397448278999e-01,
   3.06161699786838301793e-17,
   1.57079632679489655800e+00,
-  3.14159265358979311600e+00};
+  3.14159265358979311600e+00,
+  1.44269504088896338700e+00 * 64.0,
+  6.93147180369123816490e-01 / 64.0,
+  1.90821492927058770002e-10 / 64.0};
 
 // ---- sincos ----------------------------------------------------------------------------------------
 DHJ_CONSTANT double kSin[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
@@ -243,21 +246,27 @@ DHJ_FM double log_(double x) { return log_ratio(x, 1.0); }
 // log(w) = e ln2 - log(r_i) + log1p(f r_i - 1) for w = 2^e f, f in [1,2), i = top 6 mantissa bits, r_i ~ 1/f:
 // |f r_i - 1| <= 2^-7, so a degree-7 Taylor polynomial of log1p is exact to 2e-18.  No division (log_ratio spends
 // 8 FP64 instructions on one) and no exponent alignment: 12 FP64 + ~7 integer instructions.  Absolute error
-// <= 2e-16 max(1, |log w|).  The table (1 KB) is read with a per-lane index, so the kernels keep it in shared
-// memory.  w must be a positive normal number; NaN / inf give NaN.
+// <= 2e-16 max(1, |log w|).  w must be a positive normal number; NaN / inf give NaN.
 struct LogEntry { double r, l; };
+// both lookup tables (1.5 KB); read with per-lane indices, so the kernels keep a copy in shared memory
+struct Tables {
+  LogEntry log[64];        // log_tab: {r_i, -log r_i}
+  double exp2[64];         // exp_tab: 2^(j/64)
+};
 #if defined(__CUDACC__)
-__device__ const LogEntry kLogTable[64] = {
+__device__ const Tables kTables = {{
 #else
-static const LogEntry kLogTable[64] = {
+static const Tables kTables = {{
 #endif
 #include "dhj_logtable.inc"
-};
+}, {
+#include "dhj_exptable.inc"
+}};
 
-DHJ_FM double log_tab(double w, const LogEntry* __restrict__ tab) {
+DHJ_FM double log_tab(double w, const Tables* __restrict__ tab) {
   const int hi = hi32(w);
   const int e = ((hi >> 20) & 0x7ff) - 1023;
-  const LogEntry t = tab[(hi >> 14) & 63];
+  const LogEntry t = tab->log[(hi >> 14) & 63];
   const double f = from_hilo((hi & 0x000fffff) | 0x3ff00000, lo32(w));
   const double ep = fma(f, t.r, -1.0);
   double q = 1.0 / 7.0;
@@ -267,6 +276,36 @@ DHJ_FM double log_tab(double w, const LogEntry* __restrict__ tab) {
   const double ef = (double)e;
   const double res = fma(ef, kS.Ln2HiFull, t.l) + fma(ef, kS.Ln2LoFull, l1p);
   return res + (w - w);                     // NaN or inf in -> NaN out (the bit surgery above would launder them)
+}
+
+// ---- table-driven exp ------------------------------------------------------------------------------
+// exp(x) = 2^m * 2^(j/64) * exp(r), n = rint(64 x / ln 2) = 64 m + j, |r| <= ln2/128: the polynomial shrinks from
+// degree 11 to 5 (r + r^2 q(r), q minimax of degree 3: 4.4e-18), 11 FP64 instructions instead of 17.  <= 1 ulp.
+// Same range rules as exp_core / exp_ / exp_neg.
+DHJ_CONSTANT double kExpT[4] = {0.49999999999985070688, 0.16666666666658138209, 0.041666707395194626581,
+                                0.0083333420599960430757};
+
+DHJ_FM double exp_tab_core(double x, const Tables* __restrict__ tab) {
+  const double t = fma(x, kS.Log2e64, kRoundMagic);
+  const int n = lo32(t);
+  const double nf = t - kRoundMagic;
+  double r = fma(-nf, kS.Ln2Hi64, x);
+  r = fma(-nf, kS.Ln2Lo64, r);
+  const double s = tab->exp2[n & 63];
+  double q = kExpT[3];
+  q = fma(q, r, kExpT[2]); q = fma(q, r, kExpT[1]); q = fma(q, r, kExpT[0]);
+  const double p = fma(r * r, q, r);
+  return fma(s, p, s) * from_hilo(((n >> 6) + 1023) << 20, 0);
+}
+DHJ_FM double exp_tab(double x, const Tables* __restrict__ tab) {
+  double res = exp_tab_core(x, tab);
+  res = (x < -708.0) ? 0.0 : res;
+  res = (x > 709.08) ? (double)INFINITY : res;
+  return res;
+}
+DHJ_FM double exp_tab_neg(double x, const Tables* __restrict__ tab) {
+  const double res = exp_tab_core(x, tab);
+  return (x < -708.0) ? 0.0 : res;
 }
 
 // ---- atan2 -----------------------------------------------------------------------------------------

@@ -32,7 +32,7 @@ struct PriceArgs {
 __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(SliceView v, PriceArgs a) {
   __shared__ BatchSmem sm;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  load_log_table(sm.ltab, tid);
+  load_log_table(&sm.ltab, tid);
   const long long n_items = a.P * (long long)v.n_slices;
   const long long n_batches = (n_items + kBatchItems - 1) / kBatchItems;
   for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
       if (lane < kBatchMaxStrikes) warp_partial[lane] = 0.0;
       __syncwarp();
       const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
-      if (reg_mask) contract_pass(it, it.pass, it.cth, it.sth, reg_mask, v.n_cos, tid, sm.stage[warp], sm.ltab, warp_partial);
+      if (reg_mask) contract_pass(it, it.pass, it.cth, it.sth, reg_mask, v.n_cos, tid, sm.stage[warp], &sm.ltab, warp_partial);
       unsigned todo = it.valid_mask & it.bind_mask;          // rare: strikes with their own (a, b)
       while (todo) {
         const int j = __ffs(todo) - 1;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
         __syncthreads();
         // the task code indexes cth/sth by strike: point it at the single extra entry
         contract_pass(it, sm.extra_pass, &sm.extra_cth - j, &sm.extra_sth - j, 1u << j, v.n_cos, tid, sm.stage[warp],
-                      sm.ltab, warp_partial);
+                      &sm.ltab, warp_partial);
       }
     }
     __syncthreads();
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
 __global__ void __launch_bounds__(kBatchThreads, DHJ_DENSE_MINB) k_price_dense(SliceView v, PriceArgs a) {
   __shared__ DenseSmem sm;
   const int tid = threadIdx.x;
-  load_log_table(sm.ltab, tid);
+  load_log_table(&sm.ltab, tid);
   const long long n_items = a.P * (long long)v.n_slices;
   for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
     const long long p = item / v.n_slices;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kBatchThreads, 6) k_loss_batch(SliceView v, Lo
   __shared__ double s_price[kBatchItems][kBatchMaxStrikes];
   __shared__ double s_feller[kBatchItems];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  load_log_table(sm.ltab, tid);
+  load_log_table(&sm.ltab, tid);
   const int nS = v.n_slices;
   const long long n_batches = (a.n_units + a.units_per_batch - 1) / a.units_per_batch;
   for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kBatchThreads, 6) k_loss_batch(SliceView v, Lo
       if (lane < kBatchMaxStrikes) warp_partial[lane] = 0.0;
       __syncwarp();
       const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
-      if (reg_mask) contract_pass(it, it.pass, it.cth, it.sth, reg_mask, v.n_cos, tid, sm.stage[warp], sm.ltab, warp_partial);
+      if (reg_mask) contract_pass(it, it.pass, it.cth, it.sth, reg_mask, v.n_cos, tid, sm.stage[warp], &sm.ltab, warp_partial);
       unsigned todo = it.valid_mask & it.bind_mask;
       while (todo) {
         const int j = __ffs(todo) - 1;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kBatchThreads, 6) k_loss_batch(SliceView v, Lo
         }
         __syncthreads();
         contract_pass(it, sm.extra_pass, &sm.extra_cth - j, &sm.extra_sth - j, 1u << j, v.n_cos, tid, sm.stage[warp],
-                      sm.ltab, warp_partial);
+                      &sm.ltab, warp_partial);
       }
     }
     __syncthreads();
@@ -342,7 +342,7 @@ __global__ void k_cf(const double* __restrict__ params, double r, double q, doub
   const SetConsts s = make_set_consts(m, r, q);
   const double u = u_in[i];
   double xr, xi;
-  cf_exponent(s, u, tau, s.lam * tau, fm::kLogTable, &xr, &xi);
+  cf_exponent(s, u, tau, s.lam * tau, &fm::kTables, &xr, &xi);
   double sn, cs;
   fm::sincos_(xi, &sn, &cs);
   const double mag = fm::exp_(xr);

@@ -170,7 +170,7 @@ DHJ_HD PassConsts make_pass_consts(const SetConsts& s, double a, double b, doubl
 struct FactorTerms { double Ar, Ai, Bvr, Bvi; };
 
 DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
-                                 const fm::LogEntry* __restrict__ ltab) {
+                                 const fm::Tables* __restrict__ ltab) {
   const double kap = s.kappa[j];
   const double bi = -(s.rs[j] * u);                 // Im beta
   const double s2u = s.s2[j] * u;
@@ -191,7 +191,7 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
   const double dr = pos ? t : fabs(other);
   const double di = pos ? other : copysign(t, zi);
   // E = exp(-d T)
-  const double er = fm::exp_neg(-dr * T);
+  const double er = fm::exp_tab_neg(-dr * T, ltab);
   double sn, cs;
   fm::sincos_(-di * T, &sn, &cs);
   const double Er = er * cs, Ei = er * sn;
@@ -225,7 +225,7 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
 // exponent X of cf_heston * cf_jump = exp(X) at frequency u  (double_heston.py:82-96):
 //   X = ((A0 + A1) + A2) + B1 v01 + B2 v02  +  lamT (exp(i u mu - hsj2 u^2) - 1),  A0 = i (drift u) T
 // The two factors run through ONE rolled copy of heston_factor (instruction-cache footprint).
-DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, const fm::LogEntry* __restrict__ ltab,
+DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, const fm::Tables* __restrict__ ltab,
                         double* xr_out, double* xi_out) {
   double aR = 0.0, aI = (s.drift * u) * T;
   double b1r = 0.0, b1i = 0.0, b2r = 0.0, b2i = 0.0;
@@ -241,7 +241,7 @@ DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, con
   }
   double xr = (aR + b1r) + b2r;
   double xi = (aI + b1i) + b2i;
-  const double ej = fm::exp_neg(-(s.hsj2 * (u * u)));
+  const double ej = fm::exp_tab_neg(-(s.hsj2 * (u * u)), ltab);
   double sj, cj;
   fm::sincos_(u * s.mu, &sj, &cj);
   xr = fma(lamT, fma(ej, cj, -1.0), xr);
@@ -260,7 +260,7 @@ struct KTerm {
   double t3;     // (u * sin(u (b-a))) * e^b
 };
 
-DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k, const fm::LogEntry* __restrict__ ltab) {
+DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k, const fm::Tables* __restrict__ ltab) {
   KTerm t;
   // u = (k*pi)/(b-a): quotient from the precomputed reciprocal plus one correction step
   const double kpi = (double)k * kPi;
@@ -271,7 +271,7 @@ DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k, const fm
   cf_exponent(s, u, p.T, p.lamT, ltab, &xr, &xi);
   // Re( cf_heston * cf_jump * e^{-i u a} ) with the three exponentials merged
   // (the k = 0 weight 1/2 of double_heston.py:188 is folded in here: scaling by 2^-1 commutes exactly)
-  t.G = (fm::exp_(xr) * fm::cos_(fma(-u, p.a, xi))) * ((k == 0) ? 0.5 : 1.0);
+  t.G = (fm::exp_tab(xr, ltab) * fm::cos_(fma(-u, p.a, xi))) * ((k == 0) ? 0.5 : 1.0);
   // sin / cos of fl(u (b-a)) = k pi + delta, |delta| <~ 1e-13: sin = (-1)^k delta, cos = (-1)^k exactly in
   // double (what libm returns for this argument), with delta from a two-term pi
   const double kf = (double)k;

@@ -45,7 +45,7 @@ static double price_one(const Params& m, double S0, double K, double T, double r
       for (int lane = 0; lane < 32; ++lane) {
         const int k = k0 + 32 * w + lane;
         KCoef c; c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
-        if (k < N) c = make_kcoef(make_kterm(s, p, k, fm::kLogTable), p, k);
+        if (k < N) c = make_kcoef(make_kterm(s, p, k, &fm::kTables), p, k);
         P[lane] = c.P; Q[lane] = c.Q; R[lane] = c.R; a1[lane] = c.a1; a2[lane] = c.a2; a3[lane] = c.P; g0[lane] = c.g0;
       }
       const double A1 = butterfly_total(a1), A2 = butterfly_total(a2), A3 = butterfly_total(a3), G0 = butterfly_total(g0);
@@ -102,7 +102,7 @@ void emu_cf(const double* params, double r, double q, double tau, const double* 
     // w chosen so that u_k = (k*pi)/w reproduces us[i] for k = 1 is not exact; evaluate the factors directly
     double u = us[i];
     double xr, xi;
-    cf_exponent(s, u, tau, s.lam * tau, fm::kLogTable, &xr, &xi);
+    cf_exponent(s, u, tau, s.lam * tau, &fm::kTables, &xr, &xi);
     re[i] = exp(xr) * cos(xi);
     im[i] = exp(xr) * sin(xi);
   }

@@ -26,6 +26,7 @@ def fmlib():
     D = ndpointer(np.float64, flags="C")
     lib.fm_sincos.argtypes = [D, ctypes.c_int, D, D]
     lib.fm_exp.argtypes = [D, ctypes.c_int, D]
+    lib.fm_exp_tab.argtypes = [D, ctypes.c_int, D]
     lib.fm_log_ratio.argtypes = [D, D, ctypes.c_int, D]
     lib.fm_atan2.argtypes = [D, D, ctypes.c_int, D]
     lib.fm_log_tab.argtypes = [D, ctypes.c_int, D]
@@ -65,28 +66,29 @@ def _one(lib, name, *args):
     if name == "sincos":
         x = np.array([args[0]]); s, c = np.empty(1), np.empty(1)
         lib.fm_sincos(x, 1, s, c); return s[0], c[0]
-    if name == "exp":
-        x = np.array([args[0]]); o = np.empty(1); lib.fm_exp(x, 1, o); return o[0]
+    if name in ("exp", "exp_tab"):
+        x = np.array([args[0]]); o = np.empty(1); getattr(lib, "fm_" + name)(x, 1, o); return o[0]
     if name == "atan2":
         o = np.empty(1); lib.fm_atan2(np.array([args[0]]), np.array([args[1]]), 1, o); return o[0]
     if name == "log_ratio":
         o = np.empty(1); lib.fm_log_ratio(np.array([args[0]]), np.array([args[1]]), 1, o); return o[0]
 
 
-def test_exp(fmlib):
+@pytest.mark.parametrize("name", ["exp", "exp_tab"])
+def test_exp(fmlib, name):
     rng = np.random.default_rng(2)
     x = np.ascontiguousarray(np.concatenate([rng.uniform(-700, 709, 3000), rng.uniform(-40, 5, 3000),
                                              rng.uniform(-1e-3, 1e-3, 500), [0.0, -745.0, -708.5, 709.0, 1.0, -1.0]]))
     o = np.empty_like(x)
-    fmlib.fm_exp(x, x.size, o)
+    getattr(fmlib, "fm_" + name)(x, x.size, o)
     e = ulp_err(o, [mp.exp(mp.mpf(float(v))) for v in x])
     normal = x > -708
     assert e[normal].max() <= 1.0, e[normal].max()
     assert (o[~normal] == 0.0).all()                             # below the smallest normal: flushed to zero
-    assert _one(fmlib, "exp", -np.inf) == 0.0 and _one(fmlib, "exp", -800.0) == 0.0
-    assert _one(fmlib, "exp", np.inf) == np.inf and _one(fmlib, "exp", 710.0) == np.inf
-    assert _one(fmlib, "exp", -707.9) > 0.0
-    assert np.isnan(_one(fmlib, "exp", np.nan))
+    assert _one(fmlib, name, -np.inf) == 0.0 and _one(fmlib, name, -800.0) == 0.0
+    assert _one(fmlib, name, np.inf) == np.inf and _one(fmlib, name, 710.0) == np.inf
+    assert _one(fmlib, name, -707.9) > 0.0
+    assert np.isnan(_one(fmlib, name, np.nan))
 
 
 def test_log_ratio(fmlib):
