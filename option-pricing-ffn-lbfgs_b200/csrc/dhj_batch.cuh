@@ -35,7 +35,7 @@ constexpr int kBatchMaxStrikes = 8;
 struct ItemRec {
   SetConsts set;
   PassConsts pass;                 // regular pass: (a0, b0)
-  double a0, b0, S0, disc;
+  double S0, disc;                 // (the regular range (a0, b0) is pass.a, pass.b)
   double K[kBatchMaxStrikes], x[kBatchMaxStrikes], ex[kBatchMaxStrikes];
   double cth[kBatchMaxStrikes], sth[kBatchMaxStrikes];      // cos / sin of theta_j = u_1 (x_j - a0)
   unsigned valid_mask, bind_mask, call_mask;
@@ -59,6 +59,7 @@ struct PriceArgs;                  // dhj_kernels.cuh
 // every block copies the log table into its shared memory once
 __device__ __forceinline__ void load_log_table(fm::Tables* dst, int tid) {
   if (tid < 64) { dst->log[tid] = fm::kTables.log[tid]; dst->exp2[tid] = fm::kTables.exp2[tid]; }
+  if (tid < 65) dst->atan64[tid] = fm::kTables.atan64[tid];
 }
 
 // u_1 = (1*pi)/(b-a), the rotation step's frequency (same correction step as make_kterm)
@@ -75,7 +76,7 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
   double a0, b0;
   truncation_range(m, T, v.r, v.L, &a0, &b0);
   rec.pass = make_pass_consts(rec.set, a0, b0, T);
-  rec.a0 = a0; rec.b0 = b0; rec.S0 = S0;
+  rec.S0 = S0;
   rec.disc = fm::exp_(-v.r * T);
   const int o_lo = v.slice_off[s_idx], cnt = v.slice_off[s_idx + 1] - o_lo;
   unsigned bind = 0, call = 0;

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
         todo &= todo - 1;
         __syncthreads();
         if (tid == 0) {
-          sm.extra_pass = make_pass_consts(it.set, py_min(it.a0, it.x[j] - 0.1), py_max(it.b0, it.x[j] + 0.1),
+          sm.extra_pass = make_pass_consts(it.set, py_min(it.pass.a, it.x[j] - 0.1), py_max(it.pass.b, it.x[j] + 0.1),
                                            it.pass.T);
           fm::sincos_(u_one(sm.extra_pass) * (it.x[j] - sm.extra_pass.a), &sm.extra_sth, &sm.extra_cth);
         }
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kBatchThreads, 6) k_loss_batch(SliceView v, Lo
         todo &= todo - 1;
         __syncthreads();
         if (tid == 0) {
-          sm.extra_pass = make_pass_consts(it.set, py_min(it.a0, it.x[j] - 0.1), py_max(it.b0, it.x[j] + 0.1),
+          sm.extra_pass = make_pass_consts(it.set, py_min(it.pass.a, it.x[j] - 0.1), py_max(it.pass.b, it.x[j] + 0.1),
                                            it.pass.T);
           fm::sincos_(u_one(sm.extra_pass) * (it.x[j] - sm.extra_pass.a), &sm.extra_sth, &sm.extra_cth);
         }

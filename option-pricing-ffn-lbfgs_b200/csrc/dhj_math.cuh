@@ -213,7 +213,7 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
   // log(D/(2d)) : modulus from |D|^2/(4|d|^2) with |d|^2 = |z| = h ; argument from D*conj(d)
   // (log of the reciprocal ratio through the table-driven log: 4|z| / |D|^2 is one multiply away)
   const double lr = -0.5 * fm::log_tab((4.0 * h) * inD, ltab);
-  const double li = fm::atan2_nz(fma(Di, dr, -(Dr * di)), fma(Dr, dr, Di * di));
+  const double li = fm::atan2_tab_nz(fma(Di, dr, -(Dr * di)), fma(Dr, dr, Di * di), ltab);
   FactorTerms f;
   f.Ar = s.c[j] * fma(mr, T, -2.0 * lr);
   f.Ai = s.c[j] * fma(mi, T, -2.0 * li);

@@ -29,6 +29,7 @@ def fmlib():
     lib.fm_exp_tab.argtypes = [D, ctypes.c_int, D]
     lib.fm_log_ratio.argtypes = [D, D, ctypes.c_int, D]
     lib.fm_atan2.argtypes = [D, D, ctypes.c_int, D]
+    lib.fm_atan2_tab.argtypes = [D, D, ctypes.c_int, D]
     lib.fm_log_tab.argtypes = [D, ctypes.c_int, D]
     lib.fm_div.argtypes = [D, D, ctypes.c_int, D]
     lib.fm_rcp.argtypes = [D, ctypes.c_int, D]
@@ -68,8 +69,8 @@ def _one(lib, name, *args):
         lib.fm_sincos(x, 1, s, c); return s[0], c[0]
     if name in ("exp", "exp_tab"):
         x = np.array([args[0]]); o = np.empty(1); getattr(lib, "fm_" + name)(x, 1, o); return o[0]
-    if name == "atan2":
-        o = np.empty(1); lib.fm_atan2(np.array([args[0]]), np.array([args[1]]), 1, o); return o[0]
+    if name in ("atan2", "atan2_tab"):
+        o = np.empty(1); getattr(lib, "fm_" + name)(np.array([args[0]]), np.array([args[1]]), 1, o); return o[0]
     if name == "log_ratio":
         o = np.empty(1); lib.fm_log_ratio(np.array([args[0]]), np.array([args[1]]), 1, o); return o[0]
 
@@ -125,7 +126,8 @@ def test_log_tab(fmlib):
     assert np.isnan(ob).all()
 
 
-def test_atan2(fmlib):
+@pytest.mark.parametrize("name", ["atan2", "atan2_tab"])
+def test_atan2(fmlib, name):
     rng = np.random.default_rng(4)
     n = 6000
     y = rng.standard_normal(n) * np.exp(rng.uniform(-10, 10, n))
@@ -134,12 +136,12 @@ def test_atan2(fmlib):
     x[:8] = [1.0, 1.0, 0.0, 0.0, -1.0, -1.0, 1.0, -1.0]
     y, x = np.ascontiguousarray(y), np.ascontiguousarray(x)
     o = np.empty(n)
-    fmlib.fm_atan2(y, x, n, o)
+    getattr(fmlib, "fm_" + name)(y, x, n, o)
     e = ulp_err(o[8:], [mp.atan2(mp.mpf(float(a)), mp.mpf(float(b))) for a, b in zip(y[8:], x[8:])])
     assert e.max() <= 2.0, e.max()
     assert np.array_equal(o[:8], np.arctan2(y[:8], x[:8])) or np.abs(o[:8] - np.arctan2(y[:8], x[:8])).max() <= 5e-16
     assert np.signbit(o[1]) and o[5] == -np.pi
-    assert np.isnan(_one(fmlib, "atan2", np.nan, 1.0)) and np.isnan(_one(fmlib, "atan2", 1.0, np.nan))
+    assert np.isnan(_one(fmlib, name, np.nan, 1.0)) and np.isnan(_one(fmlib, name, 1.0, np.nan))
 
 
 def test_div_rcp_sqrt(fmlib):
