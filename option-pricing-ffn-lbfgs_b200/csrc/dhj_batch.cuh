@@ -1,21 +1,21 @@
 // dhj_batch.cuh — throughput kernel for grids / option lists with at most 8 strikes per maturity slice
 // (the 15-option grid of C2 / C4 / the generator / the calibrator's market).
 //
-// Decomposition: ONE THREAD PER COSINE INDEX k, a block of 128 threads walks a batch of
+// Decomposition: ONE LANE PER COSINE INDEX k, a block of 128 threads walks a batch of
 // 32 items (item = one (parameter set, maturity slice)):
 //   phase 1  thread t < 32 prepares item t ALONE: parameters (optionally exp/tanh transform), per-set
 //            constants, truncation range, pass constants, the slice's strikes (K, log(K/S0), exp(.),
 //            binding flags) -> shared memory.  The prologue is therefore executed once per item by one
 //            lane instead of redundantly by every lane of a warp (it was ~10 % of the warp-per-item
 //            kernel's instructions).
-//   phase 2  for each item, all 128 threads evaluate the CF at their own k (constants are broadcast
-//            reads from shared memory; the KTerm lives in registers and is consumed at once by the
-//            <= 8 strikes of the slice); each warp reduces its <= 8 partial prices by shuffles and
-//            parks them in shared memory — no block barrier per item.
-//   phase 3  after one barrier, thread t adds the four warps' partials of (item, strike) t and writes
-//            the discounted price.
+//   phase 2  each WARP takes every fourth item and walks its cosine terms 32 at a time: lane = k within
+//            the block of 32 (constants are broadcast reads from shared memory; the KTerm lives in
+//            registers and is consumed at once by the <= 8 strikes of the slice); the <= 8 prices
+//            accumulate in registers and are written by the warp itself — no block barrier, no
+//            partial sums in shared memory.  Walking k in order lets the trigonometric factors that
+//            are linear in k advance by rotation (contract_pass).
 // A strike whose +-0.1 widening binds (double_heston.py:135-137) is contracted in an extra pass of
-// phase 2 with its own (a,b): rare, uniform across the block.
+// phase 2 with its own (a,b): rare, set up by lane 0 of the warp.
 #pragma once
 #include "dhj_engine.cuh"
 
@@ -24,7 +24,7 @@ namespace dhj {
 constexpr int kBatchThreads = 128;
 constexpr int kBatchWarps = kBatchThreads / 32;
 #ifndef DHJ_BATCH_ITEMS
-#define DHJ_BATCH_ITEMS 32
+#define DHJ_BATCH_ITEMS 28
 #endif
 constexpr int kBatchItems = DHJ_BATCH_ITEMS;
 constexpr int kBatchMaxStrikes = 8;
@@ -34,38 +34,63 @@ constexpr int kBatchMaxStrikes = 8;
 
 struct ItemRec {
   SetConsts set;
-  PassConsts pass;                 // regular pass: (a0, b0)
-  double S0, disc;                 // (the regular range (a0, b0) is pass.a, pass.b)
+  PassConsts pass;                 // regular pass: (a0, b0) = (pass.a, pass.b)
+  double S0, disc;
+  double cmu, smu;                 // cos / sin(32 u_1 mu): the jump term's rotation from one block of 32 k to the next
   double K[kBatchMaxStrikes], x[kBatchMaxStrikes], ex[kBatchMaxStrikes];
   double cth[kBatchMaxStrikes], sth[kBatchMaxStrikes];      // cos / sin of theta_j = u_1 (x_j - a0)
+  double c32[kBatchMaxStrikes], s32[kBatchMaxStrikes];      // cos / sin of 32 theta_j
   unsigned valid_mask, bind_mask, call_mask;
   int o_lo;                        // first option (slice order) of the slice
   long long out_row;               // p * M
 };
 
-struct CoefStage { double P[32], Q[32], R[32]; };   // one warp's k-block of strike-independent coefficients
+// one warp's k-block of strike-independent coefficients P, Q, R.  Between two blocks of k the same slots park the
+// lanes' rotation state (P, Q = cos / sin(u_k mu); R, X = the segment start's cos / sin), so that it does not
+// occupy registers while the characteristic function is evaluated.  A1, A2, A3 accumulate each lane's share of
+// the strike-independent sums over all blocks of a pass (reduced once per pass, not once per block).
+struct CoefStage {
+  double P[32], Q[32], R[32], X[32];
+  double A1[32], A2[32], A3[32];
+  double g0;
+};
+
+// pass of a strike whose +-0.1 widening binds: its own (a, b) and the rotation steps that go with it
+struct ExtraPass {
+  PassConsts pass;
+  double cth, sth, c32, s32, cmu, smu;
+};
 
 struct BatchSmem {
   ItemRec items[kBatchItems];
-  PassConsts extra_pass;           // pass constants of a binding strike
-  double extra_cth, extra_sth;     // and its rotation step
+  ExtraPass extra[kBatchWarps];
   CoefStage stage[kBatchWarps];
-  fm::Tables ltab;                 // fm::log_tab / exp_tab tables (per-lane index: shared memory, not the constant bank)
-  double partial[kBatchItems][kBatchWarps][kBatchMaxStrikes];
+  fm::Tables ltab;                 // fm::log_tab / exp_tab / atan2_tab tables (per-lane index: shared memory, not the constant bank)
 };
 
 struct PriceArgs;                  // dhj_kernels.cuh
 
-// every block copies the log table into its shared memory once
+// every block copies the lookup tables into its shared memory once
 __device__ __forceinline__ void load_log_table(fm::Tables* dst, int tid) {
   if (tid < 64) { dst->log[tid] = fm::kTables.log[tid]; dst->exp2[tid] = fm::kTables.exp2[tid]; }
   if (tid < 65) dst->atan64[tid] = fm::kTables.atan64[tid];
 }
 
-// u_1 = (1*pi)/(b-a), the rotation step's frequency (same correction step as make_kterm)
+// u_1 = (1*pi)/(b-a), the rotation step's frequency (same correction step as u_of_k)
 __device__ __forceinline__ double u_one(const PassConsts& p) {
   const double q0 = kPi * p.rw;
   return fma(fma(-p.w, q0, kPi), p.rw, q0);
+}
+
+// rotation steps of one pass: theta = u_1 (x - a) per strike, and the jump term's 32 u_1 mu
+__device__ __forceinline__ void strike_rotation(const PassConsts& p, double x, double* cth, double* sth, double* c32,
+                                                double* s32) {
+  const double th = u_one(p) * (x - p.a);
+  fm::sincos_(th, sth, cth);
+  fm::sincos_(32.0 * th, s32, c32);
+}
+__device__ __forceinline__ void jump_rotation(const PassConsts& p, double mu, double* cmu, double* smu) {
+  fm::sincos_((32.0 * u_one(p)) * mu, smu, cmu);
 }
 
 // phase 1 for one item, executed by a single thread
@@ -78,6 +103,7 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
   rec.pass = make_pass_consts(rec.set, a0, b0, T);
   rec.S0 = S0;
   rec.disc = fm::exp_(-v.r * T);
+  jump_rotation(rec.pass, rec.set.mu, &rec.cmu, &rec.smu);
   const int o_lo = v.slice_off[s_idx], cnt = v.slice_off[s_idx + 1] - o_lo;
   unsigned bind = 0, call = 0;
 #pragma unroll 1
@@ -86,7 +112,7 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
     if (v.scale_by_spot) K = K * S0 / 100.0;
     const StrikeConsts sc = make_strike_consts(K, S0);
     rec.K[j] = sc.K; rec.x[j] = sc.x; rec.ex[j] = sc.ex;
-    fm::sincos_(u_one(rec.pass) * (sc.x - a0), &rec.sth[j], &rec.cth[j]);
+    strike_rotation(rec.pass, sc.x, &rec.cth[j], &rec.sth[j], &rec.c32[j], &rec.s32[j]);
     if (((sc.x - 0.1) < a0) || ((sc.x + 0.1) > b0)) bind |= 1u << j;
     if (v.call[o_lo + j]) call |= 1u << j;
   }
@@ -95,48 +121,114 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
   rec.o_lo = o_lo; rec.out_row = out_row;
 }
 
-// phase 2 body for one pass of one warp: CF at this lane's k -> strike-independent coefficients in the warp's
-// stage; four shuffle reductions (A1, A2, A3, g0); then the rotation tasks: lane = (strike j, segment s) with
-// 8-term segments, reduced over the 4 segments by two shuffles and accumulated into the warp's partial.
+// The quantities that are trigonometric functions of an angle LINEAR in k — the jump term's (cos, sin)(u_k mu)
+// and the contraction segments' start (cos, sin)(k theta_j) — are evaluated exactly in the first block of 32 k
+// and then advanced from block to block by one plane rotation (4 FP64 instructions instead of a 19 + 17
+// instruction sincos); every kReseed-th block starts from an exact evaluation again (error growth <= kReseed ulp).
+constexpr int kReseed = 8;
+
+__device__ __forceinline__ void rotate(double& c, double& s, double cr, double sr) {
+  const double c2 = fma(c, cr, -(s * sr)), s2 = fma(s, cr, c * sr);
+  c = c2; s = s2;
+}
+
+// One pass of ONE WARP over all cosine terms of an item, 32 at a time: CF at this lane's k -> strike-independent
+// coefficients in the warp's stage; then the rotation tasks: lane = (strike j, segment s) with 8-term segments,
+// reduced over the 4 segments by two shuffles and accumulated in `acc` of the lanes (j, 0).  The sums A1, A2, A3
+// (and g0) do not depend on the strike: each lane accumulates its share over the blocks and the warp reduces
+// them once at the end of the pass.
 __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConsts& pc, const double* __restrict__ cth,
-                                              const double* __restrict__ sth, unsigned mask, int n_cos, int tid,
-                                              CoefStage& st, const fm::Tables* __restrict__ ltab,
-                                              double* __restrict__ warp_partial) {
+                                              const double* __restrict__ sth, const double* __restrict__ c32,
+                                              const double* __restrict__ s32, const double* __restrict__ cmu_smu,
+                                              unsigned mask, int n_cos, int lane, CoefStage& st,
+                                              const fm::Tables* __restrict__ ltab, double& acc) {
   constexpr int kSeg = 8, kNumSeg = 32 / kSeg;
-  const int lane = tid & 31;
+  // A1, A2 feed calls, A3 puts (uniform per pass)
+  const bool any_call = (it.call_mask & mask) != 0, any_put = (~it.call_mask & mask) != 0;
+  st.A1[lane] = 0.0; st.A2[lane] = 0.0; st.A3[lane] = 0.0;     // each lane owns its slots
+  int blk = 0;
 #pragma unroll 1
-  for (int k0 = 0; k0 < n_cos; k0 += kBatchThreads) {
-    const int k = k0 + tid;
-    KCoef c;
-    c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
-    if (k < n_cos) c = make_kcoef(make_kterm(it.set, pc, k, ltab), pc, k);
+  for (int k0 = 0; k0 < n_cos; k0 += 32, ++blk) {
+    const int k = k0 + lane;
+    const bool exact = (blk % kReseed) == 0;               // uniform
+    const double u = u_of_k(pc, k);
+    double cj = 1.0, sj = 0.0;
+    KTerm t = make_kterm_f(it.set, pc, k, ltab, u, [&](double* cj_out, double* sj_out) {
+      if (exact) fm::sincos_(u * it.set.mu, &sj, &cj);
+      else { cj = st.P[lane]; sj = st.Q[lane]; rotate(cj, sj, cmu_smu[0], cmu_smu[1]); }
+      *cj_out = cj; *sj_out = sj;
+    });
+    t.G = (k < n_cos) ? t.G : 0.0;                           // ragged last block: every coefficient is a multiple of G
+    const KCoef c = make_kcoef(t, pc, k);
+    if (any_call) { st.A1[lane] += c.a1; st.A2[lane] += c.a2; }
+    if (any_put) st.A3[lane] += c.P;
+    if (k == 0) st.g0 = c.g0;
+    double cs = 1.0, sn = 0.0;
+    if (!exact) { cs = st.R[lane]; sn = st.X[lane]; }
     __syncwarp();
     st.P[lane] = c.P; st.Q[lane] = c.Q; st.R[lane] = c.R;
-    // A1, A2 feed calls, A3 puts (uniform per pass); g0 is non-zero only in the lane that holds k = 0
-    const bool any_call = (it.call_mask & mask) != 0, any_put = (~it.call_mask & mask) != 0;
-    const double A1 = any_call ? warp_sum(c.a1) : 0.0, A2 = any_call ? warp_sum(c.a2) : 0.0;
-    const double A3 = any_put ? warp_sum(c.P) : 0.0;
-    const double g0 = __shfl_sync(kFullMask, c.g0, 0);
     __syncwarp();
     // task of this lane
     const int j = lane / kNumSeg, s = lane - j * kNumSeg;
-    const bool active = (mask >> j) & 1u;
     double val = 0.0;
-    if (active) {
-      const int kstart = (k - lane) + s * kSeg;                    // absolute k of the segment's first term
-      const double kpi = (double)kstart * kPi;
-      const double q0 = kpi * pc.rw;
-      const double u0 = fma(fma(-pc.w, q0, kpi), pc.rw, q0);
-      double sn, cs;
-      fm::sincos_(u0 * (it.x[j] - pc.a), &sn, &cs);
+    if ((mask >> j) & 1u) {
+      if (exact) fm::sincos_(u_of_k(pc, k0 + s * kSeg) * (it.x[j] - pc.a), &sn, &cs);
+      else rotate(cs, sn, c32[j], s32[j]);
       double spq, sr;
       segment_sums(st.P + s * kSeg, st.Q + s * kSeg, st.R + s * kSeg, kSeg, cs, sn, cth[j], sth[j], &spq, &sr);
       val = it.K[j] * sr - (it.S0 * it.ex[j]) * spq;
-      if (s == 0) val += strike_const_part((it.call_mask >> j) & 1u, it.S0, it.K[j], it.x[j], pc, A1, A2, A3, g0);
     }
     val += __shfl_xor_sync(kFullMask, val, 1);
     val += __shfl_xor_sync(kFullMask, val, 2);
-    if (active && s == 0) warp_partial[j] += val;
+    acc += val;                                              // meaningful in the lanes (j, 0) of active strikes
+    __syncwarp();                                            // the coefficients have been consumed: park the state
+    st.P[lane] = cj; st.Q[lane] = sj; st.R[lane] = cs; st.X[lane] = sn;
+  }
+  // strike-independent sums of the pass, then the constant part of each strike
+  const double A1 = any_call ? warp_sum(st.A1[lane]) : 0.0, A2 = any_call ? warp_sum(st.A2[lane]) : 0.0;
+  const double A3 = any_put ? warp_sum(st.A3[lane]) : 0.0;
+  __syncwarp();
+  const double g0 = st.g0;
+  const int j = lane / kNumSeg;
+  if ((mask >> j) & 1u)
+    acc += strike_const_part((it.call_mask >> j) & 1u, it.S0, it.K[j], it.x[j], pc, A1, A2, A3, g0);
+}
+
+// phase 2 for a batch of `cnt_items` prepared items: warp w prices items w, w + 4, ... on its own — no block
+// barrier, no partial sums in shared memory; sink(i, j, item, price) receives each price from lane 4 j.
+// Strikes with their own (a, b) get an extra pass each (rare), set up by lane 0 in the warp's ExtraPass.
+template <class Sink>
+__device__ __forceinline__ void run_batch(BatchSmem& sm, const SliceView& v, int cnt_items, int tid, Sink sink) {
+  const int warp = tid >> 5, lane = tid & 31;
+  ExtraPass& ex = sm.extra[warp];
+#pragma unroll 1
+  for (int i = warp; i < cnt_items; i += kBatchWarps) {
+    const ItemRec& it = sm.items[i];
+    double acc = 0.0;
+    const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
+    if (reg_mask)
+      contract_pass(it, it.pass, it.cth, it.sth, it.c32, it.s32, &it.cmu, reg_mask, v.n_cos, lane,
+                    sm.stage[warp], &sm.ltab, acc);
+    unsigned todo = it.valid_mask & it.bind_mask;            // uniform: the masks live in shared memory
+    while (todo) {
+      const int jb = __ffs(todo) - 1;
+      todo &= todo - 1;
+      __syncwarp();
+      if (lane == 0) {
+        ex.pass = make_pass_consts(it.set, py_min(it.pass.a, it.x[jb] - 0.1), py_max(it.pass.b, it.x[jb] + 0.1),
+                                   it.pass.T);
+        strike_rotation(ex.pass, it.x[jb], &ex.cth, &ex.sth, &ex.c32, &ex.s32);
+        jump_rotation(ex.pass, it.set.mu, &ex.cmu, &ex.smu);
+      }
+      __syncwarp();
+      // the task code indexes the rotation steps by strike: point it at the single extra entry
+      double acc_b = 0.0;
+      contract_pass(it, ex.pass, &ex.cth - jb, &ex.sth - jb, &ex.c32 - jb, &ex.s32 - jb, &ex.cmu, 1u << jb,
+                    v.n_cos, lane, sm.stage[warp], &sm.ltab, acc_b);
+      if ((lane >> 2) == jb) acc = acc_b;
+    }
+    const int j = lane >> 2;
+    if ((lane & 3) == 0 && ((it.valid_mask >> j) & 1u)) sink(i, j, it, it.disc * acc);
   }
 }
 

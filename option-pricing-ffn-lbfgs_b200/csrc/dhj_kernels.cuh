@@ -31,7 +31,7 @@ struct PriceArgs {
 // Throughput variant of k_price for slices of <= 8 strikes: see dhj_batch.cuh.
 __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(SliceView v, PriceArgs a) {
   __shared__ BatchSmem sm;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   load_log_table(&sm.ltab, tid);
   const long long n_items = a.P * (long long)v.n_slices;
   const long long n_batches = (n_items + kBatchItems - 1) / kBatchItems;
@@ -50,42 +50,10 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
                    p * (long long)v.n_options);
     }
     __syncthreads();
-    // ---- phase 2: one thread per cosine index ----------------------------------------------------
-#pragma unroll 1
-    for (int i = 0; i < cnt_items; ++i) {
-      const ItemRec& it = sm.items[i];
-      double* warp_partial = sm.partial[i][warp];
-      if (lane < kBatchMaxStrikes) warp_partial[lane] = 0.0;
-      __syncwarp();
-      const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
-      if (reg_mask) contract_pass(it, it.pass, it.cth, it.sth, reg_mask, v.n_cos, tid, sm.stage[warp], &sm.ltab, warp_partial);
-      unsigned todo = it.valid_mask & it.bind_mask;          // rare: strikes with their own (a, b)
-      while (todo) {
-        const int j = __ffs(todo) - 1;
-        todo &= todo - 1;
-        __syncthreads();
-        if (tid == 0) {
-          sm.extra_pass = make_pass_consts(it.set, py_min(it.pass.a, it.x[j] - 0.1), py_max(it.pass.b, it.x[j] + 0.1),
-                                           it.pass.T);
-          fm::sincos_(u_one(sm.extra_pass) * (it.x[j] - sm.extra_pass.a), &sm.extra_sth, &sm.extra_cth);
-        }
-        __syncthreads();
-        // the task code indexes cth/sth by strike: point it at the single extra entry
-        contract_pass(it, sm.extra_pass, &sm.extra_cth - j, &sm.extra_sth - j, 1u << j, v.n_cos, tid, sm.stage[warp],
-                      &sm.ltab, warp_partial);
-      }
-    }
-    __syncthreads();
-    // ---- phase 3: add the warps' partials, discount, store -----------------------------------------
-    for (int t = tid; t < cnt_items * kBatchMaxStrikes; t += kBatchThreads) {
-      const int i = t / kBatchMaxStrikes, j = t - i * kBatchMaxStrikes;
-      const ItemRec& it = sm.items[i];
-      if (it.valid_mask & (1u << j)) {
-        const double* q = sm.partial[i][0] + j;
-        const double sum = ((q[0] + q[kBatchMaxStrikes]) + q[2 * kBatchMaxStrikes]) + q[3 * kBatchMaxStrikes];
-        a.out[it.out_row + v.pos[it.o_lo + j]] = it.disc * sum;
-      }
-    }
+    // ---- phase 2: a warp per item, a lane per cosine index; the warp writes its prices -------------------
+    run_batch(sm, v, cnt_items, tid, [&](int, int j, const ItemRec& it, double price) {
+      a.out[it.out_row + v.pos[it.o_lo + j]] = price;
+    });
     __syncthreads();
   }
 }
@@ -180,7 +148,7 @@ __global__ void __launch_bounds__(kBatchThreads, 6) k_loss_batch(SliceView v, Lo
   __shared__ BatchSmem sm;
   __shared__ double s_price[kBatchItems][kBatchMaxStrikes];
   __shared__ double s_feller[kBatchItems];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   load_log_table(&sm.ltab, tid);
   const int nS = v.n_slices;
   const long long n_batches = (a.n_units + a.units_per_batch - 1) / a.units_per_batch;
@@ -206,40 +174,8 @@ __global__ void __launch_bounds__(kBatchThreads, 6) k_loss_batch(SliceView v, Lo
       if (s == 0) s_feller[ul] = feller_penalty(m);
     }
     __syncthreads();
-    // ---- phase 2 (identical to k_price_batch) --------------------------------------------------------
-#pragma unroll 1
-    for (int i = 0; i < cnt_items; ++i) {
-      const ItemRec& it = sm.items[i];
-      double* warp_partial = sm.partial[i][warp];
-      if (lane < kBatchMaxStrikes) warp_partial[lane] = 0.0;
-      __syncwarp();
-      const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
-      if (reg_mask) contract_pass(it, it.pass, it.cth, it.sth, reg_mask, v.n_cos, tid, sm.stage[warp], &sm.ltab, warp_partial);
-      unsigned todo = it.valid_mask & it.bind_mask;
-      while (todo) {
-        const int j = __ffs(todo) - 1;
-        todo &= todo - 1;
-        __syncthreads();
-        if (tid == 0) {
-          sm.extra_pass = make_pass_consts(it.set, py_min(it.pass.a, it.x[j] - 0.1), py_max(it.pass.b, it.x[j] + 0.1),
-                                           it.pass.T);
-          fm::sincos_(u_one(sm.extra_pass) * (it.x[j] - sm.extra_pass.a), &sm.extra_sth, &sm.extra_cth);
-        }
-        __syncthreads();
-        contract_pass(it, sm.extra_pass, &sm.extra_cth - j, &sm.extra_sth - j, 1u << j, v.n_cos, tid, sm.stage[warp],
-                      &sm.ltab, warp_partial);
-      }
-    }
-    __syncthreads();
-    // ---- phase 3: prices -> shared memory --------------------------------------------------------------
-    for (int t = tid; t < cnt_items * kBatchMaxStrikes; t += kBatchThreads) {
-      const int i = t / kBatchMaxStrikes, j = t - i * kBatchMaxStrikes;
-      const ItemRec& it = sm.items[i];
-      if (it.valid_mask & (1u << j)) {
-        const double* q = sm.partial[i][0] + j;
-        s_price[i][j] = it.disc * (((q[0] + q[kBatchMaxStrikes]) + q[2 * kBatchMaxStrikes]) + q[3 * kBatchMaxStrikes]);
-      }
-    }
+    // ---- phase 2 (as k_price_batch): prices -> shared memory ------------------------------------------
+    run_batch(sm, v, cnt_items, tid, [&](int i, int j, const ItemRec&, double price) { s_price[i][j] = price; });
     __syncthreads();
     // ---- phase 4: one thread per unit: loss, and the gradient when a state's stencil is complete ----------
     if (tid < n_units_here) {

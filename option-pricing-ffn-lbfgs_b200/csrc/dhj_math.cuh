@@ -225,8 +225,11 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
 // exponent X of cf_heston * cf_jump = exp(X) at frequency u  (double_heston.py:82-96):
 //   X = ((A0 + A1) + A2) + B1 v01 + B2 v02  +  lamT (exp(i u mu - hsj2 u^2) - 1),  A0 = i (drift u) T
 // The two factors run through ONE rolled copy of heston_factor (instruction-cache footprint).
-DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, const fm::Tables* __restrict__ ltab,
-                        double* xr_out, double* xi_out) {
+// jump_trig(&cj, &sj) supplies cos / sin(u mu) AFTER the two Heston factors (where register pressure peaks): the
+// batch kernel advances them by rotation from one block of k to the next instead of evaluating a sincos
+template <class JumpTrig>
+DHJ_HD void cf_exponent_f(const SetConsts& s, double u, double T, double lamT, const fm::Tables* __restrict__ ltab,
+                          JumpTrig jump_trig, double* xr_out, double* xi_out) {
   double aR = 0.0, aI = (s.drift * u) * T;
   double b1r = 0.0, b1i = 0.0, b2r = 0.0, b2i = 0.0;
 #ifdef DHJ_UNROLL_FACTORS
@@ -242,11 +245,16 @@ DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, con
   double xr = (aR + b1r) + b2r;
   double xi = (aI + b1i) + b2i;
   const double ej = fm::exp_tab_neg(-(s.hsj2 * (u * u)), ltab);
-  double sj, cj;
-  fm::sincos_(u * s.mu, &sj, &cj);
+  double cj, sj;
+  jump_trig(&cj, &sj);
   xr = fma(lamT, fma(ej, cj, -1.0), xr);
   xi = fma(lamT, ej * sj, xi);
   *xr_out = xr; *xi_out = xi;
+}
+
+DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, const fm::Tables* __restrict__ ltab,
+                        double* xr_out, double* xi_out) {
+  cf_exponent_f(s, u, T, lamT, ltab, [&](double* cj, double* sj) { fm::sincos_(u * s.mu, sj, cj); }, xr_out, xi_out);
 }
 
 // everything the strike loop needs for one k
@@ -260,15 +268,21 @@ struct KTerm {
   double t3;     // (u * sin(u (b-a))) * e^b
 };
 
-DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k, const fm::Tables* __restrict__ ltab) {
-  KTerm t;
-  // u = (k*pi)/(b-a): quotient from the precomputed reciprocal plus one correction step
+// u_k = (k*pi)/(b-a): quotient from the precomputed reciprocal plus one correction step
+DHJ_HD double u_of_k(const PassConsts& p, int k) {
   const double kpi = (double)k * kPi;
   const double q0 = kpi * p.rw;
-  const double u = fma(fma(-p.w, q0, kpi), p.rw, q0);
+  return fma(fma(-p.w, q0, kpi), p.rw, q0);
+}
+
+// u = u_k; jump_trig as in cf_exponent_f
+template <class JumpTrig>
+DHJ_HD KTerm make_kterm_f(const SetConsts& s, const PassConsts& p, int k, const fm::Tables* __restrict__ ltab,
+                          double u, JumpTrig jump_trig) {
+  KTerm t;
   t.u = u;
   double xr, xi;
-  cf_exponent(s, u, p.T, p.lamT, ltab, &xr, &xi);
+  cf_exponent_f(s, u, p.T, p.lamT, ltab, jump_trig, &xr, &xi);
   // Re( cf_heston * cf_jump * e^{-i u a} ) with the three exponentials merged
   // (the k = 0 weight 1/2 of double_heston.py:188 is folded in here: scaling by 2^-1 commutes exactly)
   t.G = (fm::exp_tab(xr, ltab) * fm::cos_(fma(-u, p.a, xi))) * ((k == 0) ? 0.5 : 1.0);
@@ -283,6 +297,11 @@ DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k, const fm
   t.inv1 = fm::rcp(1.0 + u * u);
   t.invu = (k == 0) ? 0.0 : fm::rcp(u);
   return t;
+}
+
+DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k, const fm::Tables* __restrict__ ltab) {
+  const double u = u_of_k(p, k);
+  return make_kterm_f(s, p, k, ltab, u, [&](double* cj, double* sj) { fm::sincos_(u * s.mu, sj, cj); });
 }
 
 // strike-dependent constants of one option
