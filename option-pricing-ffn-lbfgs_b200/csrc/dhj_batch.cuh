@@ -199,7 +199,10 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
 // Strikes with their own (a, b) get an extra pass each (rare), set up by lane 0 in the warp's ExtraPass.
 template <class Sink>
 __device__ __forceinline__ void run_batch(BatchSmem& sm, const SliceView& v, int cnt_items, int tid, Sink sink) {
-  const int warp = tid >> 5, lane = tid & 31;
+  // the shuffle tells ptxas that the warp index is warp-uniform: the item loop and everything addressed through it
+  // then run on the uniform datapath (constants via LDCU into uniform registers, address arithmetic off the
+  // vector pipe)
+  const int warp = __shfl_sync(kFullMask, tid >> 5, 0), lane = tid & 31;
   ExtraPass& ex = sm.extra[warp];
 #pragma unroll 1
   for (int i = warp; i < cnt_items; i += kBatchWarps) {
