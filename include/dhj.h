@@ -150,6 +150,20 @@ DHJ_API int dhj_lbfgs_tell(dhj_lbfgs* opt, int64_t n_active, const double* f, co
 /* any output may be NULL: x[n][dim], f[n], nit[n], nfev[n], status[n] */
 DHJ_API int dhj_lbfgs_result(const dhj_lbfgs* opt, double* x, double* f, int32_t* nit, int32_t* nfev, int32_t* status);
 
+/* ---- synthetic generator: the host-side draw stream -------------------------------------------
+ * Replaces the per-sample Python loop of generate_synthetic_calibrations
+ * (/root/reference/src/data/synthetic_generator.py:98-142: 13 np.random.uniform, one np.random.normal(0.0003,
+ * 0.01) for the spot return when i > 0, 15 np.random.normal(0, 0.02) of price noise, AR(1) smoothing :105-109,
+ * spot walk :112-116) with the same arithmetic on NumPy's legacy MT19937 stream, bit for bit.  Host only, no
+ * context.  State in: np.random.get_state() -> (key[624], pos, has_gauss, cached_gaussian); state out: the same
+ * four values after the draws, for np.random.set_state().  Outputs: params[n][n_params], spots[n],
+ * noise[n][n_noise] (the N(0, noise_sd) factors; market = model + noise * model, :141-142). */
+DHJ_API int dhj_generator_draws(const uint32_t* mt_key, int32_t mt_pos, int32_t has_gauss, double cached_gauss,
+                                int64_t n, int32_t n_params, const double* lo, const double* hi, double persistence,
+                                double spot0, double ret_mean, double ret_sd, double noise_sd, int32_t n_noise,
+                                double* params, double* spots, double* noise, uint32_t* out_key, int32_t* out_pos,
+                                int32_t* out_has_gauss, double* out_cached_gauss);
+
 /* ---- measurement ---------------------------------------------------------------------------- */
 /* Runs a register-resident FP64 FMA-chain kernel on every SM and reports the sustained DFMA rate
  * (2 flop per FMA) — the denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 figure). */

@@ -25,6 +25,7 @@ EXPORTS = (
     "dhj_market_create", "dhj_market_destroy", "dhj_loss_batch", "dhj_loss_fd", "dhj_market_prices",
     "dhj_cf", "dhj_truncation_range", "dhj_chi_psi", "dhj_fp64_peak",
     "dhj_lbfgs_create", "dhj_lbfgs_destroy", "dhj_lbfgs_ask", "dhj_lbfgs_tell", "dhj_lbfgs_result",
+    "dhj_generator_draws",
 )
 
 
@@ -89,6 +90,10 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.dhj_lbfgs_ask.argtypes = [_c_vp, ctypes.POINTER(_c_i64), _I64, _F64]
         lib.dhj_lbfgs_tell.argtypes = [_c_vp, _c_i64, _F64, _F64]
         lib.dhj_lbfgs_result.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]
+        _U32 = ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+        lib.dhj_generator_draws.argtypes = [_U32, _c_i32, _c_i32, _c_f64, _c_i64, _c_i32, _F64, _F64, _c_f64, _c_f64,
+                                            _c_f64, _c_f64, _c_f64, _c_i32, _F64, _F64, _F64, _U32,
+                                            ctypes.POINTER(_c_i32), ctypes.POINTER(_c_i32), ctypes.POINTER(_c_f64)]
         for name in EXPORTS:
             if name not in ("dhj_last_error",):
                 getattr(lib, name).restype = ctypes.c_int
@@ -396,6 +401,31 @@ class BatchLBFGS:
 
 _default_ctx: Context | None = None
 _default_lock = threading.Lock()
+
+
+def generator_draws(n, lo, hi, persistence, spot0, ret_mean, ret_sd, noise_sd, n_noise):
+    """The synthetic generator's draw stream (dhj_generator_draws) on NumPy's GLOBAL legacy RandomState: reads
+    `np.random.get_state()`, produces params[n, len(lo)], spots[n], noise[n, n_noise] exactly as the reference's
+    per-sample `np.random.uniform` / `np.random.normal` calls would (synthetic_generator.py:98-142), and writes
+    the advanced state back with `np.random.set_state()`.  Host only: needs the library, not a GPU."""
+    lib = load_library()
+    kind, key, pos, has_gauss, cached = np.random.get_state()
+    if kind != "MT19937":
+        raise NativeError(f"np.random global state is {kind}, expected the legacy MT19937")
+    lo, hi = _f64(lo), _f64(hi)
+    n = int(n)
+    params, spots, noise = np.empty((n, lo.size)), np.empty(n), np.empty((n, int(n_noise)))
+    key_in = np.ascontiguousarray(key, dtype=np.uint32)
+    key_out = np.empty(624, dtype=np.uint32)
+    pos_out, hg_out, cached_out = _c_i32(), _c_i32(), _c_f64()
+    rc = lib.dhj_generator_draws(key_in, int(pos), int(has_gauss), float(cached), n, lo.size, lo, hi,
+                                 float(persistence), float(spot0), float(ret_mean), float(ret_sd), float(noise_sd),
+                                 int(n_noise), params, spots, noise, key_out, ctypes.byref(pos_out),
+                                 ctypes.byref(hg_out), ctypes.byref(cached_out))
+    if rc != 0:
+        raise NativeError(f"dhj_generator_draws failed ({rc})")
+    np.random.set_state(("MT19937", key_out, pos_out.value, hg_out.value, cached_out.value))
+    return params, spots, noise
 
 
 def default_context() -> Context:

@@ -12,8 +12,13 @@ noise; /root/reference/src/data/synthetic_generator.py:98-142).  The draws do no
 so they are hoisted out of the pricing loop and the n x 15 prices are then computed by one call of
 `dhj.Context.price_grid` (strikes scaled by spot as in :125).
 
-For datasets too large for a list of Python objects use `generate_synthetic_arrays`, which returns /
-fills flat arrays.
+The draw stream itself (sequential: one MT19937 generator, AR(1) smoothing, spot walk) runs in the library
+too (`dhj_generator_draws`, bit-identical to the per-sample `np.random` calls): 0.7 s per million samples
+instead of 19 s of Python loop.
+
+For datasets too large for a list of Python objects: `generate_synthetic_arrays` returns flat
+arrays (optionally written as .npz or as a directory of .npy files that can be memory-mapped), and
+`SyntheticCalibrationSet` presents such arrays as a lazy sequence of `CalibrationResult` objects.
 """
 import pickle
 import sys
@@ -28,7 +33,7 @@ sys.path.insert(0, str(Path(__file__).parent.parent.parent))
 
 from lbfgs_calibrator import CalibrationResult  # noqa: E402
 from double_heston import DoubleHeston  # noqa: E402,F401
-from dhj import default_context  # noqa: E402
+from dhj import default_context, generator_draws  # noqa: E402
 
 # parameter ranges, in RNG draw order (synthetic_generator.py:75-89)
 PARAM_RANGES = {
@@ -56,33 +61,100 @@ def _trading_dates(n):
 
 
 def _draw_inputs(n):
-    """Host recurrence: parameters (AR(1)-smoothed), spots (random walk) and price-noise factors.
-
-    Three global-RNG calls per sample instead of the reference's 29 scalar ones, consuming the stream in the
-    same order (13 uniforms, [1 normal], 15 normals): bit-identical values."""
+    """Host recurrence: parameters (AR(1)-smoothed), spots (random walk) and price-noise factors, drawn from the
+    global NumPy RNG in the reference's order (per sample 13 uniforms, [1 normal], 15 normals) by the library's
+    restatement of NumPy's legacy generator: bit-identical values and final RNG state (SURVEY §8a row 15;
+    tests/test_host_logic.py compares it with the per-sample np.random calls)."""
     names = list(PARAM_RANGES)
     lo = np.array([v[0] for v in PARAM_RANGES.values()])
     hi = np.array([v[1] for v in PARAM_RANGES.values()])
-    n_opt = MATURITIES.size * STRIKES.size
-    params = np.empty((n, len(names)))
-    spots = np.empty(n)
-    noise = np.empty((n, n_opt))
-    for i in range(n):
-        fresh = np.random.uniform(lo, hi)
-        if i > 0:
-            fresh = PERSISTENCE * params[i - 1] + (1 - PERSISTENCE) * fresh
-            spots[i] = spots[i - 1] * (1 + np.random.normal(0.0003, 0.01))
-        else:
-            spots[i] = SPOT_BASE
-        params[i] = fresh
-        noise[i] = np.random.normal(0, 0.02, size=n_opt)
+    params, spots, noise = generator_draws(n, lo, hi, PERSISTENCE, SPOT_BASE, 0.0003, 0.01, 0.02,
+                                           MATURITIES.size * STRIKES.size)
     return names, params, spots, noise
+
+
+_ARRAY_KEYS = ('params', 'spots', 'strikes', 'maturities', 'model_prices', 'market_prices', 'losses')
+
+
+def _save_arrays(data, save_path):
+    """`x.npz` -> one archive; anything else -> a directory of .npy files (memory-mappable)."""
+    save_path = str(save_path)
+    if save_path.endswith('.npz'):
+        np.savez(save_path, **{k: np.asarray(v) for k, v in data.items()})
+        return
+    Path(save_path).mkdir(parents=True, exist_ok=True)
+    for k in _ARRAY_KEYS:
+        np.save(Path(save_path) / f'{k}.npy', data[k])
+    np.save(Path(save_path) / 'param_names.npy', np.asarray(data['param_names']))
+
+
+class SyntheticCalibrationSet:
+    """Lazy sequence view of a flat synthetic dataset: `len(ds)`, `ds[i]` -> `CalibrationResult` built on demand
+    (same fields as the objects `generate_synthetic_calibrations` returns), slicing -> another view.  Holds only
+    the arrays — O(1) Python objects however many samples; with `load(path, mmap=True)` not even those."""
+
+    def __init__(self, data):
+        self.data = data
+        self.param_names = [str(s) for s in data['param_names']]
+
+    @classmethod
+    def load(cls, path, mmap=True):
+        path = str(path)
+        if path.endswith('.npz'):
+            z = np.load(path)
+            return cls({k: z[k] for k in z.files})
+        d = {k: np.load(Path(path) / f'{k}.npy', mmap_mode='r' if mmap else None) for k in _ARRAY_KEYS}
+        d['param_names'] = np.load(Path(path) / 'param_names.npy')
+        return cls(d)
+
+    def save(self, path):
+        _save_arrays(self.data, path)
+
+    def __len__(self):
+        return int(self.data['spots'].shape[0])
+
+    def __getitem__(self, i):
+        d = self.data
+        if isinstance(i, slice):
+            sub = {k: (d[k][i] if k != 'maturities' else d[k]) for k in _ARRAY_KEYS}
+            sub['param_names'] = d['param_names']
+            sub['_first'] = d.get('_first', 0) + (i.indices(len(self))[0] if len(self) else 0)
+            assert i.step in (None, 1), "contiguous slices only"
+            return SyntheticCalibrationSet(sub)
+        n = len(self)
+        if i < 0:
+            i += n
+        if not 0 <= i < n:
+            raise IndexError(i)
+        mats = d['maturities']
+        options = [{'strike': d['strikes'][i, j], 'maturity': mats[j], 'price': d['market_prices'][i, j],
+                    'option_type': 'call'} for j in range(mats.size)]
+        return CalibrationResult(
+            date=_trading_date(d.get('_first', 0) + i), spot=d['spots'][i], risk_free=RISK_FREE,
+            parameters={name: d['params'][i, k] for k, name in enumerate(self.param_names)},
+            market_prices=np.array(d['market_prices'][i]), model_prices=np.array(d['model_prices'][i]),
+            market_options=options, final_loss=d['losses'][i],
+            calibration_time=None, success=True, iterations=None,
+            message='Synthetic data (not from real calibration)')
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def _trading_date(i):
+    """The i-th weekday on or after 2022-01-03 (a Monday), in closed form (:59-67).  Python's datetime ends in
+    year 9999 (sample ~2.08 M; the reference's own date loop raises there): later samples are labelled by index."""
+    try:
+        return (datetime(2022, 1, 3) + timedelta(days=7 * (i // 5) + i % 5)).strftime('%Y-%m-%d')
+    except OverflowError:
+        return f'2022-01-03+{i}bd'
 
 
 def generate_synthetic_arrays(n_samples, ctx=None, save_path=None):
     """Flat-array form of the generator: dict of params[n,13], spots[n], strikes[n,15], maturities[15],
     model_prices[n,15], market_prices[n,15], losses[n] (same values as the object form).  With `save_path` the
-    arrays are also written as one .npz — the on-disk form for datasets too large for a pickle of Python
+    arrays are also written — `*.npz`: one archive; any other path: a directory of .npy files that
+    `SyntheticCalibrationSet.load` memory-maps — the on-disk form for datasets too large for a pickle of Python
     objects."""
     ctx = ctx or default_context()
     names, params, spots, noise = _draw_inputs(n_samples)
@@ -95,7 +167,7 @@ def generate_synthetic_arrays(n_samples, ctx=None, save_path=None):
             'maturities': np.repeat(MATURITIES, STRIKES.size), 'model_prices': model,
             'market_prices': market, 'losses': np.mean(rel ** 2, axis=1)}
     if save_path is not None:
-        np.savez(save_path, **{k: np.asarray(v) for k, v in data.items()})
+        _save_arrays(data, save_path)
     return data
 
 

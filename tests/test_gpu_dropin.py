@@ -245,6 +245,20 @@ def test_warm_start_hook_and_flat_arrays(mods, golden, tmp_path):
     assert rel_err(data["model_prices"], g["model_prices"]).max() <= 1e-10
     again = np.load(path)
     assert np.array_equal(again["market_prices"], data["market_prices"]) and again["params"].shape == (20, 13)
+    # directory-of-.npy sink + lazy CalibrationResult view against the object form
+    np.random.seed(42)
+    objs = gen.generate_synthetic_calibrations(20, save_path=str(tmp_path / "objs.pkl"))
+    np.random.seed(42)
+    gen.generate_synthetic_arrays(20, save_path=str(tmp_path / "flat_dir"))
+    ds = gen.SyntheticCalibrationSet.load(tmp_path / "flat_dir")
+    assert len(ds) == 20 and isinstance(ds.data["params"], np.memmap)
+    for i in (0, 7, 19, -1):
+        a_, b_ = ds[i], objs[i]
+        assert a_.date == b_.date and a_.spot == b_.spot and a_.parameters == b_.parameters
+        assert np.array_equal(a_.market_prices, b_.market_prices) and a_.final_loss == b_.final_loss
+        assert a_.market_options == b_.market_options and a_.message == b_.message
+    assert ds[5:9][1].date == objs[6].date and len(ds[5:9]) == 4
+    assert gen.SyntheticCalibrationSet.load(path)[3].spot == objs[3].spot
 
 
 def test_reference_suite_section_4_verbatim(mods, golden):

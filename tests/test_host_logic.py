@@ -117,6 +117,43 @@ def test_generator_host_recurrence(dropins, golden):
     assert np.array_equal(g["model_prices"] + noise * g["model_prices"], g["market_prices"])
     assert gen._trading_dates(20) == list(g["dates"])
     assert gen._trading_dates(0) == []
+    assert [gen._trading_date(i) for i in range(20)] == list(g["dates"])
+
+
+def test_generator_draws_match_numpy_stream(dropins):
+    """dhj_generator_draws (csrc/dhj_draws.cpp) against the reference's own per-sample np.random calls
+    (synthetic_generator.py:98-142): same values bit for bit, same generator state afterwards — also when the
+    state carries a cached gaussian, across an MT19937 refill, and for n = 0 / 1."""
+    _, _, gen = dropins
+    lo = np.array([v[0] for v in gen.PARAM_RANGES.values()])
+    hi = np.array([v[1] for v in gen.PARAM_RANGES.values()])
+
+    def numpy_stream(n):
+        params, spots, noise = np.empty((n, 13)), np.empty(n), np.empty((n, 15))
+        for i in range(n):
+            fresh = np.array([np.random.uniform(a, b) for a, b in zip(lo, hi)])      # 13 scalar draws, as the reference
+            if i > 0:
+                fresh = 0.9 * params[i - 1] + (1 - 0.9) * fresh
+                spots[i] = spots[i - 1] * (1 + np.random.normal(0.0003, 0.01))
+            else:
+                spots[i] = 100.0
+            params[i] = fresh
+            noise[i] = [np.random.normal(0, 0.02) for _ in range(15)]
+        return params, spots, noise
+
+    for seed, n, odd in ((42, 20, False), (7, 400, True), (3, 1, True), (5, 0, False)):
+        np.random.seed(seed)
+        if odd:
+            np.random.normal()                      # leaves the pair's second variate cached in the state
+        start = np.random.get_state()
+        want = numpy_stream(n)
+        end = np.random.get_state()
+        np.random.set_state(start)
+        _, *got = gen._draw_inputs(n)
+        now = np.random.get_state()
+        assert all(np.array_equal(w, g) for w, g in zip(want, got)), (seed, n)
+        assert np.array_equal(end[1], now[1]) and end[2:] == now[2:]
+        assert np.random.random() == (np.random.set_state(end), np.random.random())[1]
 
 
 def test_lockstep_evaluator_batches_requests(dropins):
