@@ -148,13 +148,19 @@ DHJ_CONSTANT ScalarConsts kS = {
   6.93147180369123816490e-01 / 64.0,
   1.90821492927058770002e-10 / 64.0,
   1.5 * 70368744177664.0,
-  -1.0 / 3.0, 0.2, -1.0 / 7.0};
+  -1.0 / 3.0, 0.2, -0.14285719394683837891};     // AtC3: -1/7 as a high word (its term is below 2^-41)
 
 // ---- sincos ----------------------------------------------------------------------------------------
-DHJ_CONSTANT double kSin[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
-                               2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10};
-DHJ_CONSTANT double kCos[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
-                               -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+// sin r = r + r z S(z), cos r = 1 - z/2 + z^2 C(z), z = r^2 <= (pi/4)^2: minimax fits (scripts/gen_poly.py imm:
+// 2.4e-17 / 1.6e-18) whose two highest coefficients are rounded to a HIGH WORD (low 32 bits zero) with the
+// rest refitted around them.  An FP64 instruction on sm_100 takes such a constant as a 32-bit immediate;
+// any other coefficient costs a constant-bank load (an issue slot) per use.
+DHJ_CONSTANT double kSin[4] = {-0.16666666666666664702, 0.0083333333333307815961, -0.00019841269836439504943,
+                               2.7557315924814562483e-6};
+constexpr double kSin4 = -2.5051093643924104981e-8, kSin5 = 1.5915335715988021548e-10;      // high-word constants
+DHJ_CONSTANT double kCos[4] = {0.041666666666666665048, -0.0013888888888887096165, 0.000024801587298387249032,
+                               -2.755731711353240655e-7};
+constexpr double kCos4 = 2.0876118611568017513e-9, kCos5 = -1.1380882347644671881e-11;      // high-word constants
 constexpr double kRoundMagic = 6755399441055744.0;     // 1.5 * 2^52: (x + magic) - magic = rint(x), low word = int
 
 // sin and cos of x, |x| <= ~1e5 (Cody-Waite with FMA; no Payne-Hanek path)
@@ -165,12 +171,12 @@ DHJ_FM void sincos_(double x, double* s_out, double* c_out) {
   double r = fma(-n, kS.Pio2Hi, x);
   r = fma(-n, kS.Pio2Mid, r);               // |n| < 2^17: the next term of pi/2 (1.5e-33 n) is far below 1 ulp
   const double z = r * r;
-  double ps = kSin[5];
-  ps = fma(ps, z, kSin[4]); ps = fma(ps, z, kSin[3]); ps = fma(ps, z, kSin[2]); ps = fma(ps, z, kSin[1]);
+  double ps = kSin5;
+  ps = fma(ps, z, kSin4); ps = fma(ps, z, kSin[3]); ps = fma(ps, z, kSin[2]); ps = fma(ps, z, kSin[1]);
   ps = fma(ps, z, kSin[0]);
   const double s = fma(r * z, ps, r);
-  double pc = kCos[5];
-  pc = fma(pc, z, kCos[4]); pc = fma(pc, z, kCos[3]); pc = fma(pc, z, kCos[2]); pc = fma(pc, z, kCos[1]);
+  double pc = kCos5;
+  pc = fma(pc, z, kCos4); pc = fma(pc, z, kCos[3]); pc = fma(pc, z, kCos[2]); pc = fma(pc, z, kCos[1]);
   pc = fma(pc, z, kCos[0]);
   const double c = fma(z, fma(z, pc, -0.5), 1.0);
   // quadrant: q odd swaps; bit 1 of q negates sin, bit 1 of (q+1) negates cos
@@ -276,8 +282,9 @@ DHJ_FM double log_tab(double w, const Tables* __restrict__ tab) {
   const LogEntry t = tab->log[(hi >> 14) & 63];
   const double f = from_hilo((hi & 0x000fffff) | 0x3ff00000, lo32(w));
   const double ep = fma(f, t.r, -1.0);
-  double q = 1.0 / 7.0;
-  q = fma(q, ep, -1.0 / 6.0); q = fma(q, ep, 0.2); q = fma(q, ep, -0.25); q = fma(q, ep, 1.0 / 3.0);
+  // 1/7 and -1/6 rounded to a high word (32-bit immediates): their terms are below 2^-42 and 2^-35 of the result
+  double q = 0.14285719394683837891;
+  q = fma(q, ep, -0.16666662693023681641); q = fma(q, ep, 0.2); q = fma(q, ep, -0.25); q = fma(q, ep, 1.0 / 3.0);
   q = fma(q, ep, -0.5);
   const double l1p = fma(ep * ep, q, ep);
   const double ef = (double)e;
@@ -287,10 +294,11 @@ DHJ_FM double log_tab(double w, const Tables* __restrict__ tab) {
 
 // ---- table-driven exp ------------------------------------------------------------------------------
 // exp(x) = 2^m * 2^(j/64) * exp(r), n = rint(64 x / ln 2) = 64 m + j, |r| <= ln2/128: the polynomial shrinks from
-// degree 11 to 5 (r + r^2 q(r), q minimax of degree 3: 4.4e-18), 11 FP64 instructions instead of 17.  <= 1 ulp.
+// degree 11 to 5 (r + r^2 q(r), q minimax of degree 3 with a high-word leading coefficient: 5e-18), 11 FP64
+// instructions instead of 17.  <= 1 ulp.
 // Same range rules as exp_core / exp_ / exp_neg.
-DHJ_CONSTANT double kExpT[4] = {0.49999999999985070688, 0.16666666666658138209, 0.041666707395194626581,
-                                0.0083333420599960430757};
+DHJ_CONSTANT double kExpT[3] = {0.49999999999985997477, 0.1666666666666058649, 0.041666707400273529831};
+constexpr double kExpT3 = 0.0083333402872085571289;                                           // high-word constant
 
 DHJ_FM double exp_tab_core(double x, const Tables* __restrict__ tab) {
   const double t = fma(x, kS.Log2e64, kRoundMagic);
@@ -299,7 +307,7 @@ DHJ_FM double exp_tab_core(double x, const Tables* __restrict__ tab) {
   double r = fma(-nf, kS.Ln2Hi64, x);
   r = fma(-nf, kS.Ln2Lo64, r);
   const double s = tab->exp2[n & 63];
-  double q = kExpT[3];
+  double q = kExpT3;
   q = fma(q, r, kExpT[2]); q = fma(q, r, kExpT[1]); q = fma(q, r, kExpT[0]);
   const double p = fma(r * r, q, r);
   return fma(s, p, s) * from_hilo(((n >> 6) + 1023) << 20, 0);
@@ -363,7 +371,7 @@ DHJ_FM double atan2_tab_impl(double y, double x, const Tables* __restrict__ tab)
   const double c = tt - kS.AtanMagic;
   const double t = div(fma(-c, mx, mn), fma(c, mn, mx));
   const double z = t * t;
-  const double p = fma(z, fma(z, kS.AtC3, kS.AtC2), kS.AtC1);
+  const double p = fma(z, fma(z, -0.14285719394683837891, kS.AtC2), kS.AtC1);   // -1/7 as a high word: immediate
   double r = tab->atan64[i] + fma(t * z, p, t);     // atan(mn/mx) in [0, pi/4]
   r = steep ? kS.PiO2 - r : r;
   r = (x < 0.0) ? kS.PiD - r : r;

@@ -47,7 +47,7 @@ def show(name, c, emax):
     print("{" + ", ".join(mp.nstr(x, 20) for x in c) + "}")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(__import__("sys").argv) == 1:
     # exp(r) = 1 + r + r^2 * q(r), |r| <= ln2/2 ; q of degree 9 (total degree 11)
     L = mp.log(2) / 2
     q = lambda r: (mp.exp(r) - 1 - r) / r ** 2 if abs(r) > mp.mpf('1e-15') else mp.mpf(1) / 2 + r / 6 + r * r / 24
@@ -55,3 +55,49 @@ if __name__ == "__main__":
     show("exp q(r) deg 9 (abs error of q; times r^2 <= 0.12)", c, e)
     c, e = remez(q, -L, L, 10)
     show("exp q(r) deg 10", c, e)
+
+
+# ---- coefficients that fit a 32-bit immediate -----------------------------------------------------------------
+# An FP64 instruction on sm_100 takes a double constant for free only as a 32-bit immediate (the high word; low
+# word zero); any other coefficient costs a constant-bank load.  The highest-order coefficients of a polynomial
+# need few bits, so they are rounded to 21 significant bits and the remaining coefficients are refitted around
+# them (python scripts/gen_poly.py imm).
+def round_hi(x):
+    import struct
+    b = struct.unpack("<Q", struct.pack("<d", float(x)))[0]
+    b = (b + 0x80000000) & 0xFFFFFFFF00000000
+    return mp.mpf(struct.unpack("<d", struct.pack("<Q", b))[0])
+
+
+def refit_with_fixed_top(f, a, b, deg, n_fixed):
+    """Minimax coefficients c_0..c_deg of f on [a,b] where the top n_fixed are rounded to a high word, one at a
+    time, and the lower ones refitted after each rounding."""
+    fixed = []
+    for step in range(n_fixed + 1):
+        d = deg - len(fixed)
+        g = lambda x: f(x) - sum(c * x ** (d + 1 + i) for i, c in enumerate(reversed(fixed)))
+        c, e = remez(g, a, b, d)
+        if step < n_fixed:
+            fixed.append(round_hi(c[-1]))
+    return c + list(reversed(fixed)), e
+
+
+def imm_main():
+    Z = (mp.pi / 4) ** 2 * mp.mpf("1.02")
+    sq = lambda z: mp.sqrt(z)
+    fs = lambda z: ((mp.sin(sq(z)) / sq(z) - 1) / z) if z > mp.mpf("1e-20") else -mp.mpf(1) / 6 + z / 120
+    c, e = refit_with_fixed_top(fs, mp.mpf(0), Z, 5, 2)
+    show("sin: (sin(r)/r - 1)/z, z = r^2 <= (pi/4)^2, top 2 coefficients 32-bit", c, e)
+    fc = lambda z: ((mp.cos(sq(z)) - 1 + z / 2) / z ** 2) if z > mp.mpf("1e-12") else mp.mpf(1) / 24 - z / 720 + z * z / 40320
+    c, e = refit_with_fixed_top(fc, mp.mpf(0), Z, 5, 2)
+    show("cos: (cos(r) - 1 + z/2)/z^2, top 2 coefficients 32-bit", c, e)
+    L = mp.log(2) / 128
+    q = lambda r: (mp.exp(r) - 1 - r) / r ** 2 if abs(r) > mp.mpf('1e-15') else mp.mpf(1) / 2 + r / 6 + r * r / 24
+    c, e = refit_with_fixed_top(q, -L, L, 3, 1)
+    show("exp_tab q(r) deg 3 on |r| <= ln2/128, top coefficient 32-bit (error of q; times r^2 <= 2.9e-5)", c, e)
+    for name, v in (("1/7", mp.mpf(1) / 7), ("-1/6", -mp.mpf(1) / 6), ("-1/7", -mp.mpf(1) / 7)):
+        print(f"// {name} as a high word: {mp.nstr(round_hi(v), 20)}")
+
+
+if __name__ == "__main__" and len(__import__("sys").argv) > 1 and __import__("sys").argv[1] == "imm":
+    imm_main()
