@@ -224,7 +224,8 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
 
 // exponent X of cf_heston * cf_jump = exp(X) at frequency u  (double_heston.py:82-96):
 //   X = ((A0 + A1) + A2) + B1 v01 + B2 v02  +  lamT (exp(i u mu - hsj2 u^2) - 1),  A0 = i (drift u) T
-// The two factors run through ONE rolled copy of heston_factor (instruction-cache footprint).
+// The two factors are unrolled: with the table-driven elementary functions the body is small enough for the
+// instruction cache, and the rolled loop's register shuffling cost more than the second copy.
 // jump_trig(&cj, &sj) supplies cos / sin(u mu) AFTER the two Heston factors (where register pressure peaks): the
 // batch kernel advances them by rotation from one block of k to the next instead of evaluating a sincos
 template <class JumpTrig>
@@ -232,11 +233,7 @@ DHJ_HD void cf_exponent_f(const SetConsts& s, double u, double T, double lamT, c
                           JumpTrig jump_trig, double* xr_out, double* xi_out) {
   double aR = 0.0, aI = (s.drift * u) * T;
   double b1r = 0.0, b1i = 0.0, b2r = 0.0, b2i = 0.0;
-#ifdef DHJ_UNROLL_FACTORS
 #pragma unroll
-#else
-#pragma unroll 1
-#endif
   for (int j = 0; j < 2; ++j) {
     const FactorTerms f = heston_factor(s, j, u, T, ltab);
     aR += f.Ar; aI += f.Ai;
