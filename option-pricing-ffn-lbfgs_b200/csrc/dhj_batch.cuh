@@ -28,8 +28,15 @@ constexpr int kBatchWarps = kBatchThreads / 32;
 #endif
 constexpr int kBatchItems = DHJ_BATCH_ITEMS;
 constexpr int kBatchMaxStrikes = 8;
+// resident blocks per SM the kernels are compiled for (register budget = 65 536 / (128 * MINB)).  Measured on C2
+// (profiles/README.md): 7 blocks at 72 registers 14.36 ms, 6 at 80 14.40, 5 at 96 14.51, 4 at 122 14.03, 3 at 140
+// 14.72 — with room for the temporaries of both Heston factors ptxas overlaps their dependent chains, which is
+// worth more than the 12 warps given up.  The loss kernel (more shared memory per block) prefers 7.
 #ifndef DHJ_BATCH_MINB
-#define DHJ_BATCH_MINB 7
+#define DHJ_BATCH_MINB 4
+#endif
+#ifndef DHJ_LOSS_MINB
+#define DHJ_LOSS_MINB 7
 #endif
 
 struct ItemRec {

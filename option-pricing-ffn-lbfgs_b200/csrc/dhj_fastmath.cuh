@@ -288,7 +288,8 @@ DHJ_FM double log_tab(double w, const Tables* __restrict__ tab) {
   q = fma(q, ep, -0.5);
   const double l1p = fma(ep * ep, q, ep);
   const double ef = (double)e;
-  const double res = fma(ef, kS.Ln2HiFull, t.l) + fma(ef, kS.Ln2LoFull, l1p);
+  // ln 2 - Ln2HiFull rounded to a high word (32-bit immediate): the 21-bit constant misses 1e-23 |e|
+  const double res = fma(ef, kS.Ln2HiFull, t.l) + fma(ef, 2.31904650766222601363e-17, l1p);
   return res + (w - w);                     // NaN or inf in -> NaN out (the bit surgery above would launder them)
 }
 

@@ -144,7 +144,7 @@ struct LossBatchArgs {
   unsigned int* counters;    // fd: [C]
 };
 
-__global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_loss_batch(SliceView v, LossBatchArgs a) {
+__global__ void __launch_bounds__(kBatchThreads, DHJ_LOSS_MINB) k_loss_batch(SliceView v, LossBatchArgs a) {
   __shared__ BatchSmem sm;
   __shared__ double s_price[kBatchItems][kBatchMaxStrikes];
   __shared__ double s_feller[kBatchItems];
