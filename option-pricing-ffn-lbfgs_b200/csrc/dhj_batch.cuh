@@ -144,6 +144,9 @@ __device__ __forceinline__ void rotate(double& c, double& s, double cr, double s
 // reduced over the 4 segments by two shuffles and accumulated in `acc` of the lanes (j, 0).  The sums A1, A2, A3
 // (and g0) do not depend on the strike: each lane accumulates its share over the blocks and the warp reduces
 // them once at the end of the pass.
+// PARK: keep the loop-carried state (rotation state, A-sum accumulators) in the stage's shared-memory slots
+// between blocks of k (kernels compiled for 72 registers) instead of in registers (the pricing kernel at 122).
+template <bool PARK>
 __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConsts& pc, const double* __restrict__ cth,
                                               const double* __restrict__ sth, const double* __restrict__ c32,
                                               const double* __restrict__ s32, const double* __restrict__ cmu_smu,
@@ -152,26 +155,35 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
   constexpr int kSeg = 8, kNumSeg = 32 / kSeg;
   // A1, A2 feed calls, A3 puts (uniform per pass)
   const bool any_call = (it.call_mask & mask) != 0, any_put = (~it.call_mask & mask) != 0;
-  st.A1[lane] = 0.0; st.A2[lane] = 0.0; st.A3[lane] = 0.0;     // each lane owns its slots
+  if (PARK) { st.A1[lane] = 0.0; st.A2[lane] = 0.0; st.A3[lane] = 0.0; }     // each lane owns its slots
+  double a1 = 0.0, a2 = 0.0, a3 = 0.0, g0_keep = 0.0;
+  double cj = 1.0, sj = 0.0, cs = 1.0, sn = 0.0;
   int blk = 0;
 #pragma unroll 1
   for (int k0 = 0; k0 < n_cos; k0 += 32, ++blk) {
     const int k = k0 + lane;
     const bool exact = (blk % kReseed) == 0;               // uniform
     const double u = u_of_k(pc, k);
-    double cj = 1.0, sj = 0.0;
     KTerm t = make_kterm_f(it.set, pc, k, ltab, u, [&](double* cj_out, double* sj_out) {
       if (exact) fm::sincos_(u * it.set.mu, &sj, &cj);
-      else { cj = st.P[lane]; sj = st.Q[lane]; rotate(cj, sj, cmu_smu[0], cmu_smu[1]); }
+      else {
+        if (PARK) { cj = st.P[lane]; sj = st.Q[lane]; }
+        rotate(cj, sj, cmu_smu[0], cmu_smu[1]);
+      }
       *cj_out = cj; *sj_out = sj;
     });
     t.G = (k < n_cos) ? t.G : 0.0;                           // ragged last block: every coefficient is a multiple of G
     const KCoef c = make_kcoef(t, pc, k);
-    if (any_call) { st.A1[lane] += c.a1; st.A2[lane] += c.a2; }
-    if (any_put) st.A3[lane] += c.P;
-    if (k == 0) st.g0 = c.g0;
-    double cs = 1.0, sn = 0.0;
-    if (!exact) { cs = st.R[lane]; sn = st.X[lane]; }
+    if (PARK) {
+      cs = 1.0; sn = 0.0;                                    // not carried in registers: reloaded below
+      if (any_call) { st.A1[lane] += c.a1; st.A2[lane] += c.a2; }
+      if (any_put) st.A3[lane] += c.P;
+      if (k == 0) st.g0 = c.g0;
+      if (!exact) { cs = st.R[lane]; sn = st.X[lane]; }
+    } else {
+      a1 += c.a1; a2 += c.a2; a3 += c.P;
+      if (blk == 0) g0_keep = __shfl_sync(kFullMask, c.g0, 0);
+    }
     __syncwarp();
     st.P[lane] = c.P; st.Q[lane] = c.Q; st.R[lane] = c.R;
     __syncwarp();
@@ -188,14 +200,17 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
     val += __shfl_xor_sync(kFullMask, val, 1);
     val += __shfl_xor_sync(kFullMask, val, 2);
     acc += val;                                              // meaningful in the lanes (j, 0) of active strikes
-    __syncwarp();                                            // the coefficients have been consumed: park the state
-    st.P[lane] = cj; st.Q[lane] = sj; st.R[lane] = cs; st.X[lane] = sn;
+    if (PARK) {
+      __syncwarp();                                          // the coefficients have been consumed: park the state
+      st.P[lane] = cj; st.Q[lane] = sj; st.R[lane] = cs; st.X[lane] = sn;
+    }
   }
   // strike-independent sums of the pass, then the constant part of each strike
-  const double A1 = any_call ? warp_sum(st.A1[lane]) : 0.0, A2 = any_call ? warp_sum(st.A2[lane]) : 0.0;
-  const double A3 = any_put ? warp_sum(st.A3[lane]) : 0.0;
+  if (PARK) { a1 = st.A1[lane]; a2 = st.A2[lane]; a3 = st.A3[lane]; }
+  const double A1 = any_call ? warp_sum(a1) : 0.0, A2 = any_call ? warp_sum(a2) : 0.0;
+  const double A3 = any_put ? warp_sum(a3) : 0.0;
   __syncwarp();
-  const double g0 = st.g0;
+  const double g0 = PARK ? st.g0 : g0_keep;
   const int j = lane / kNumSeg;
   if ((mask >> j) & 1u)
     acc += strike_const_part((it.call_mask >> j) & 1u, it.S0, it.K[j], it.x[j], pc, A1, A2, A3, g0);
@@ -204,7 +219,7 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
 // phase 2 for a batch of `cnt_items` prepared items: warp w prices items w, w + 4, ... on its own — no block
 // barrier, no partial sums in shared memory; sink(i, j, item, price) receives each price from lane 4 j.
 // Strikes with their own (a, b) get an extra pass each (rare), set up by lane 0 in the warp's ExtraPass.
-template <class Sink>
+template <bool PARK, class Sink>
 __device__ __forceinline__ void run_batch(BatchSmem& sm, const SliceView& v, int cnt_items, int tid, Sink sink) {
   // the shuffle tells ptxas that the warp index is warp-uniform: the item loop and everything addressed through it
   // then run on the uniform datapath (constants via LDCU into uniform registers, address arithmetic off the
@@ -217,7 +232,7 @@ __device__ __forceinline__ void run_batch(BatchSmem& sm, const SliceView& v, int
     double acc = 0.0;
     const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
     if (reg_mask)
-      contract_pass(it, it.pass, it.cth, it.sth, it.c32, it.s32, &it.cmu, reg_mask, v.n_cos, lane,
+      contract_pass<PARK>(it, it.pass, it.cth, it.sth, it.c32, it.s32, &it.cmu, reg_mask, v.n_cos, lane,
                     sm.stage[warp], &sm.ltab, acc);
     unsigned todo = it.valid_mask & it.bind_mask;            // uniform: the masks live in shared memory
     while (todo) {
@@ -233,7 +248,7 @@ __device__ __forceinline__ void run_batch(BatchSmem& sm, const SliceView& v, int
       __syncwarp();
       // the task code indexes the rotation steps by strike: point it at the single extra entry
       double acc_b = 0.0;
-      contract_pass(it, ex.pass, &ex.cth - jb, &ex.sth - jb, &ex.c32 - jb, &ex.s32 - jb, &ex.cmu, 1u << jb,
+      contract_pass<PARK>(it, ex.pass, &ex.cth - jb, &ex.sth - jb, &ex.c32 - jb, &ex.s32 - jb, &ex.cmu, 1u << jb,
                     v.n_cos, lane, sm.stage[warp], &sm.ltab, acc_b);
       if ((lane >> 2) == jb) acc = acc_b;
     }

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
     }
     __syncthreads();
     // ---- phase 2: a warp per item, a lane per cosine index; the warp writes its prices -------------------
-    run_batch(sm, v, cnt_items, tid, [&](int, int j, const ItemRec& it, double price) {
+    run_batch<false>(sm, v, cnt_items, tid, [&](int, int j, const ItemRec& it, double price) {
       a.out[it.out_row + v.pos[it.o_lo + j]] = price;
     });
     __syncthreads();
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_LOSS_MINB) k_loss_batch(Sli
     }
     __syncthreads();
     // ---- phase 2 (as k_price_batch): prices -> shared memory ------------------------------------------
-    run_batch(sm, v, cnt_items, tid, [&](int i, int j, const ItemRec&, double price) { s_price[i][j] = price; });
+    run_batch<true>(sm, v, cnt_items, tid, [&](int i, int j, const ItemRec&, double price) { s_price[i][j] = price; });
     __syncthreads();
     // ---- phase 4: one thread per unit: loss, and the gradient when a state's stencil is complete ----------
     if (tid < n_units_here) {
