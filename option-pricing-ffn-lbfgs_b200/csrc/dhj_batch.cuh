@@ -56,8 +56,12 @@ struct ItemRec {
 // lanes' rotation state (P, Q = cos / sin(u_k mu); R, X = the segment start's cos / sin), so that it does not
 // occupy registers while the characteristic function is evaluated.  A1, A2, A3 accumulate each lane's share of
 // the strike-independent sums over all blocks of a pass (reduced once per pass, not once per block).
+// Layout: PQ[k] = (P_k, Q_k) and R[k], for 128-bit loads in the contraction (one for P and Q, one for two consecutive
+// R); the batch kernel's four 8-term segments are read concurrently by different lanes, so each segment is shifted
+// by one 16-byte slot (PQ) / two doubles (R) to land in different banks.
 struct CoefStage {
-  double P[32], Q[32], R[32], X[32];
+  Pair PQ[36];
+  double R[40], X[32];
   double A1[32], A2[32], A3[32];
   double g0;
 };
@@ -153,6 +157,7 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
                                               unsigned mask, int n_cos, int lane, CoefStage& st,
                                               const fm::Tables* __restrict__ ltab, double& acc) {
   constexpr int kSeg = 8, kNumSeg = 32 / kSeg;
+  const int slot_pq = lane + (lane >> 3), slot_r = lane + 2 * (lane >> 3);      // padded stage slots of this lane's k
   // A1, A2 feed calls, A3 puts (uniform per pass)
   const bool any_call = (it.call_mask & mask) != 0, any_put = (~it.call_mask & mask) != 0;
   if (PARK) { st.A1[lane] = 0.0; st.A2[lane] = 0.0; st.A3[lane] = 0.0; }     // each lane owns its slots
@@ -167,7 +172,7 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
     KTerm t = make_kterm_f(it.set, pc, k, ltab, u, [&](double* cj_out, double* sj_out) {
       if (exact) fm::sincos_(u * it.set.mu, &sj, &cj);
       else {
-        if (PARK) { cj = st.P[lane]; sj = st.Q[lane]; }
+        if (PARK) { const Pair t2 = st.PQ[slot_pq]; cj = t2.x; sj = t2.y; }
         rotate(cj, sj, cmu_smu[0], cmu_smu[1]);
       }
       *cj_out = cj; *sj_out = sj;
@@ -179,13 +184,13 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
       if (any_call) { st.A1[lane] += c.a1; st.A2[lane] += c.a2; }
       if (any_put) st.A3[lane] += c.P;
       if (k == 0) st.g0 = c.g0;
-      if (!exact) { cs = st.R[lane]; sn = st.X[lane]; }
+      if (!exact) { cs = st.R[slot_r]; sn = st.X[lane]; }
     } else {
       a1 += c.a1; a2 += c.a2; a3 += c.P;
       if (blk == 0) g0_keep = __shfl_sync(kFullMask, c.g0, 0);
     }
     __syncwarp();
-    st.P[lane] = c.P; st.Q[lane] = c.Q; st.R[lane] = c.R;
+    st.PQ[slot_pq] = make_double2(c.P, c.Q); st.R[slot_r] = c.R;
     __syncwarp();
     // task of this lane
     const int j = lane / kNumSeg, s = lane - j * kNumSeg;
@@ -194,7 +199,8 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
       if (exact) fm::sincos_(u_of_k(pc, k0 + s * kSeg) * (it.x[j] - pc.a), &sn, &cs);
       else rotate(cs, sn, c32[j], s32[j]);
       double spq, sr;
-      segment_sums(st.P + s * kSeg, st.Q + s * kSeg, st.R + s * kSeg, kSeg, cs, sn, cth[j], sth[j], &spq, &sr);
+      segment_sums<kSeg>(st.PQ + s * (kSeg + 1), reinterpret_cast<const Pair*>(st.R + s * (kSeg + 2)), cs, sn, cth[j],
+                         sth[j], &spq, &sr);
       val = it.K[j] * sr - (it.S0 * it.ex[j]) * spq;
     }
     val += __shfl_xor_sync(kFullMask, val, 1);
@@ -202,7 +208,7 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
     acc += val;                                              // meaningful in the lanes (j, 0) of active strikes
     if (PARK) {
       __syncwarp();                                          // the coefficients have been consumed: park the state
-      st.P[lane] = cj; st.Q[lane] = sj; st.R[lane] = cs; st.X[lane] = sn;
+      st.PQ[slot_pq] = make_double2(cj, sj); st.R[slot_r] = cs; st.X[lane] = sn;
     }
   }
   // strike-independent sums of the pass, then the constant part of each strike

@@ -46,7 +46,7 @@ __device__ __forceinline__ void dense_pass(DenseSmem& sm, const PassConsts& pc, 
     c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
     if (k < n_cos) c = make_kcoef(make_kterm(sm.set, pc, k, &sm.ltab), pc, k);
     __syncwarp();
-    st.P[lane] = c.P; st.Q[lane] = c.Q; st.R[lane] = c.R;
+    st.PQ[lane] = make_double2(c.P, c.Q); st.R[lane] = c.R;
     const double A1 = warp_sum(c.a1), A2 = warp_sum(c.a2), A3 = warp_sum(c.P);
     const double g0 = __shfl_sync(kFullMask, c.g0, 0);
     __syncwarp();
@@ -62,7 +62,7 @@ __device__ __forceinline__ void dense_pass(DenseSmem& sm, const PassConsts& pc, 
       double sn, cs, spq, sr;
       fm::sincos_(u0 * (sm.x[t] - pc.a), &sn, &cs);
       const int ti = (single < 0) ? t : 0;
-      segment_sums(st.P, st.Q, st.R, 32, cs, sn, cth[ti], sth[ti], &spq, &sr);
+      segment_sums<32>(st.PQ, reinterpret_cast<const Pair*>(st.R), cs, sn, cth[ti], sth[ti], &spq, &sr);
       const double val = (sm.K[t] * sr - (sm.S0 * sm.ex[t]) * spq) +
                          strike_const_part(sm.call[t] != 0, sm.S0, sm.K[t], sm.x[t], pc, A1, A2, A3, g0);
       sm.partial[warp][t] += val;

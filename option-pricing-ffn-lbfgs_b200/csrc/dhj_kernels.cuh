@@ -146,7 +146,6 @@ struct LossBatchArgs {
 
 __global__ void __launch_bounds__(kBatchThreads, DHJ_LOSS_MINB) k_loss_batch(SliceView v, LossBatchArgs a) {
   __shared__ BatchSmem sm;
-  __shared__ double s_price[kBatchItems][kBatchMaxStrikes];
   __shared__ double s_feller[kBatchItems];
   const int tid = threadIdx.x;
   load_log_table(&sm.ltab, tid);
@@ -174,8 +173,9 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_LOSS_MINB) k_loss_batch(Sli
       if (s == 0) s_feller[ul] = feller_penalty(m);
     }
     __syncthreads();
-    // ---- phase 2 (as k_price_batch): prices -> shared memory ------------------------------------------
-    run_batch<true>(sm, v, cnt_items, tid, [&](int i, int j, const ItemRec&, double price) { s_price[i][j] = price; });
+    // ---- phase 2 (as k_price_batch): prices -> shared memory, in the item's ex[] slots (exp(x_j) is dead once
+    // the item's passes are done; only the warp that owns the item touches them) -----------------------------
+    run_batch<true>(sm, v, cnt_items, tid, [&](int i, int j, const ItemRec&, double price) { sm.items[i].ex[j] = price; });
     __syncthreads();
     // ---- phase 4: one thread per unit: loss, and the gradient when a state's stencil is complete ----------
     if (tid < n_units_here) {
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_LOSS_MINB) k_loss_batch(Sli
         const double* market_row = a.market + it.out_row;           // out_row = market index * M
         const int cnt = __popc(it.valid_mask);
         for (int j = 0; j < cnt; ++j) {
-          const double price = s_price[tid * nS + s][j];
+          const double price = it.ex[j];
           if (!(price > 0.0) || isinf(price)) bad = true;           // lbfgs_calibrator.py:152
           const double mk = market_row[v.pos[it.o_lo + j]];
           const double rel = (price - mk) / mk;                     // :163

@@ -340,18 +340,32 @@ DHJ_HD KCoef make_kcoef(const KTerm& t, const PassConsts& p, int k) {
 // cos/sin((k0+i) theta) advance by the three-term recurrence  t_{i+1} = 2 cos(theta) t_i - t_{i-1}  (one FMA per
 // sequence and step; the first step is a plane rotation by theta).  Its rounding error grows like i eps / sin(theta)
 // over the <= 32 steps of a segment (theta = pi (x-a)/(b-a) is >= pi * 0.1/(b-a) by the +-0.1 widening).
-DHJ_HD void segment_sums(const double* __restrict__ P, const double* __restrict__ Q, const double* __restrict__ R,
-                         int seg, double c, double s, double cth, double sth, double* sum_pq, double* sum_r) {
-  double apq = fma(Q[0], s, P[0] * c), ar = R[0] * s;
+#if defined(__CUDACC__)
+using Pair = double2;                         // 16-byte aligned: one 128-bit shared-memory load
+#else
+struct alignas(16) Pair { double x, y; };
+#endif
+
+// PQ[i] = (P, Q) of term k0 + i; RR[i] = (R of term k0 + 2i, R of term k0 + 2i + 1); SEG even.
+template <int SEG>
+DHJ_HD void segment_sums(const Pair* __restrict__ PQ, const Pair* __restrict__ RR, double c, double s, double cth,
+                         double sth, double* sum_pq, double* sum_r) {
+  Pair pq = PQ[0], rr = RR[0];
+  double apq = fma(pq.y, s, pq.x * c), ar = rr.x * s;
   double c1 = fma(c, cth, -(s * sth)), s1 = fma(s, cth, c * sth);     // (k0 + 1) theta
   const double two_c = cth + cth;
-#pragma unroll 4
-  for (int i = 1; i < seg; ++i) {
-    apq = fma(P[i], c1, apq);
-    apq = fma(Q[i], s1, apq);
-    ar = fma(R[i], s1, ar);
-    const double c2 = fma(two_c, c1, -c), s2 = fma(two_c, s1, -s);
+  pq = PQ[1];
+  apq = fma(pq.x, c1, apq); apq = fma(pq.y, s1, apq); ar = fma(rr.y, s1, ar);
+#pragma unroll 2
+  for (int i = 2; i < SEG; i += 2) {
+    double c2 = fma(two_c, c1, -c), s2 = fma(two_c, s1, -s);          // (k0 + i) theta
     c = c1; s = s1; c1 = c2; s1 = s2;
+    pq = PQ[i]; rr = RR[i >> 1];
+    apq = fma(pq.x, c1, apq); apq = fma(pq.y, s1, apq); ar = fma(rr.x, s1, ar);
+    c2 = fma(two_c, c1, -c); s2 = fma(two_c, s1, -s);                 // (k0 + i + 1) theta
+    c = c1; s = s1; c1 = c2; s1 = s2;
+    pq = PQ[i + 1];
+    apq = fma(pq.x, c1, apq); apq = fma(pq.y, s1, apq); ar = fma(rr.y, s1, ar);
   }
   *sum_pq = apq; *sum_r = ar;
 }

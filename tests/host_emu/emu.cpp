@@ -41,12 +41,14 @@ static double price_one(const Params& m, double S0, double K, double T, double r
   double partial[4] = {0, 0, 0, 0};
   for (int k0 = 0; k0 < N; k0 += 128) {
     for (int w = 0; w < 4; ++w) {
-      double P[32], Q[32], R[32], a1[32], a2[32], a3[32], g0[32];
+      Pair PQ[32];
+      alignas(16) double R[32];
+      double a1[32], a2[32], a3[32], g0[32];
       for (int lane = 0; lane < 32; ++lane) {
         const int k = k0 + 32 * w + lane;
         KCoef c; c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
         if (k < N) c = make_kcoef(make_kterm(s, p, k, &fm::kTables), p, k);
-        P[lane] = c.P; Q[lane] = c.Q; R[lane] = c.R; a1[lane] = c.a1; a2[lane] = c.a2; a3[lane] = c.P; g0[lane] = c.g0;
+        PQ[lane].x = c.P; PQ[lane].y = c.Q; R[lane] = c.R; a1[lane] = c.a1; a2[lane] = c.a2; a3[lane] = c.P; g0[lane] = c.g0;
       }
       const double A1 = butterfly_total(a1), A2 = butterfly_total(a2), A3 = butterfly_total(a3), G0 = butterfly_total(g0);
       double val[4];
@@ -54,7 +56,7 @@ static double price_one(const Params& m, double S0, double K, double T, double r
         const int kstart = k0 + 32 * w + 8 * sg;
         double sn, cs, spq, sr;
         fm::sincos_(u_of(p, kstart) * (sc.x - p.a), &sn, &cs);
-        segment_sums(P + 8 * sg, Q + 8 * sg, R + 8 * sg, 8, cs, sn, cth, sth, &spq, &sr);
+        segment_sums<8>(PQ + 8 * sg, reinterpret_cast<const Pair*>(R + 8 * sg), cs, sn, cth, sth, &spq, &sr);
         val[sg] = sc.K * sr - (S0 * sc.ex) * spq;
         if (sg == 0) val[sg] += strike_const_part(is_call != 0, S0, sc.K, sc.x, p, A1, A2, A3, G0);
       }
