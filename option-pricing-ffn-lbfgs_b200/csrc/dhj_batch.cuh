@@ -44,7 +44,7 @@ struct ItemRec {
   PassConsts pass;                 // regular pass: (a0, b0) = (pass.a, pass.b)
   double S0, disc;
   double cmu, smu;                 // cos / sin(32 u_1 mu): the jump term's rotation from one block of 32 k to the next
-  double K[kBatchMaxStrikes], x[kBatchMaxStrikes], ex[kBatchMaxStrikes];
+  double K[kBatchMaxStrikes], x[kBatchMaxStrikes], ex[kBatchMaxStrikes];      // strike, log(K/S0), S0 * exp(x)
   double cth[kBatchMaxStrikes], sth[kBatchMaxStrikes];      // cos / sin of theta_j = u_1 (x_j - a0)
   double c32[kBatchMaxStrikes], s32[kBatchMaxStrikes];      // cos / sin of 32 theta_j
   unsigned valid_mask, bind_mask, call_mask;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
     double K = strike_row[v.pos[o_lo + j]];
     if (v.scale_by_spot) K = K * S0 / 100.0;
     const StrikeConsts sc = make_strike_consts(K, S0);
-    rec.K[j] = sc.K; rec.x[j] = sc.x; rec.ex[j] = sc.ex;
+    rec.K[j] = sc.K; rec.x[j] = sc.x; rec.ex[j] = S0 * sc.ex;
     strike_rotation(rec.pass, sc.x, &rec.cth[j], &rec.sth[j], &rec.c32[j], &rec.s32[j]);
     if (((sc.x - 0.1) < a0) || ((sc.x + 0.1) > b0)) bind |= 1u << j;
     if (v.call[o_lo + j]) call |= 1u << j;
@@ -181,12 +181,13 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
     const KCoef c = make_kcoef(t, pc, k);
     if (PARK) {
       cs = 1.0; sn = 0.0;                                    // not carried in registers: reloaded below
-      if (any_call) { st.A1[lane] += c.a1; st.A2[lane] += c.a2; }
+      if (any_call) { st.A1[lane] = fma(c.P, t.t1 + t.t3, st.A1[lane]); st.A2[lane] = fma(c.R, t.sb, st.A2[lane]); }
       if (any_put) st.A3[lane] += c.P;
       if (k == 0) st.g0 = c.g0;
       if (!exact) { cs = st.R[slot_r]; sn = st.X[lane]; }
     } else {
-      a1 += c.a1; a2 += c.a2; a3 += c.P;
+      if (any_call) { a1 = fma(c.P, t.t1 + t.t3, a1); a2 = fma(c.R, t.sb, a2); }
+      if (any_put) a3 += c.P;
       if (blk == 0) g0_keep = __shfl_sync(kFullMask, c.g0, 0);
     }
     __syncwarp();
@@ -201,7 +202,7 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
       double spq, sr;
       segment_sums<kSeg>(st.PQ + s * (kSeg + 1), reinterpret_cast<const Pair*>(st.R + s * (kSeg + 2)), cs, sn, cth[j],
                          sth[j], &spq, &sr);
-      val = it.K[j] * sr - (it.S0 * it.ex[j]) * spq;
+      val = fma(it.K[j], sr, -(it.ex[j] * spq));
     }
     val += __shfl_xor_sync(kFullMask, val, 1);
     val += __shfl_xor_sync(kFullMask, val, 2);

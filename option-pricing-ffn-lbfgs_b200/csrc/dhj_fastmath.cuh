@@ -276,9 +276,10 @@ static const Tables kTables = {{
 #include "dhj_atantable.inc"
 }};
 
-DHJ_FM double log_tab(double w, const Tables* __restrict__ tab) {
+// e_off: returns log(w * 2^e_off) (the offset merges with the exponent bias: free)
+DHJ_FM double log_tab(double w, const Tables* __restrict__ tab, int e_off = 0) {
   const int hi = hi32(w);
-  const int e = ((hi >> 20) & 0x7ff) - 1023;
+  const int e = ((hi >> 20) & 0x7ff) - 1023 + e_off;
   const LogEntry t = tab->log[(hi >> 14) & 63];
   const double f = from_hilo((hi & 0x000fffff) | 0x3ff00000, lo32(w));
   const double ep = fma(f, t.r, -1.0);

@@ -78,10 +78,11 @@ DHJ_HD double feller_penalty(const Params& m) {
 // quantities that depend on the parameter set (and r, q) only
 struct SetConsts {
   double kappa[2], kk[2];      // kappa, kappa^2
+  double two_kappa[2];
   double rs[2];                // rho*sigma
-  double s2[2], inv_s2[2];     // sigma^2, fl(1/sigma^2)
+  double s2[2];                // sigma^2
+  double sv[2];                // v0/sigma^2
   double c[2];                 // kappa*theta/sigma^2
-  double v0[2];
   double drift;                // r - q - lam*(exp(mu + sj^2/2) - 1)       double_heston.py:82-83
   double lam, mu, hsj2;        // hsj2 = 0.5*sj^2
 };
@@ -93,9 +94,9 @@ DHJ_HD SetConsts make_set_consts(const Params& m, double r, double q) {
     s.kk[j] = m.kappa[j] * m.kappa[j];
     s.rs[j] = m.rho[j] * m.sigma[j];
     s.s2[j] = m.sigma[j] * m.sigma[j];
-    s.inv_s2[j] = fm::rcp(s.s2[j]);
+    s.two_kappa[j] = m.kappa[j] + m.kappa[j];
+    s.sv[j] = fm::div(m.v0[j], s.s2[j]);
     s.c[j] = fm::div(m.kappa[j] * m.theta[j], s.s2[j]);
-    s.v0[j] = m.v0[j];
   }
   s.hsj2 = 0.5 * (m.sj * m.sj);
   double comp = fm::exp_(m.mu + s.hsj2) - 1.0;
@@ -160,23 +161,25 @@ DHJ_HD PassConsts make_pass_consts(const SetConsts& s, double a, double b, doubl
 }
 
 // ---- characteristic function ----------------------------------------------------------------
-// One variance factor: returns A_j and B_j*v0_j.
+// One variance factor: A_j and B_j*v0_j.
 //   beta = kappa - i rho sigma u ;  d = sqrt(beta^2 + sigma^2 u (u+i)) ;  E = exp(-d T)
 //   m = beta - d ; pl = beta + d ; D = pl - m E          [1 - gE = D/pl ; 1 - g = 2d/pl]
 //   B = (m/sigma^2) (1-E)/(1-gE) = (m/sigma^2) (1-E) pl / D
 //   A = (kappa theta/sigma^2) (m T - 2 log((1-gE)/(1-g))) ,  (1-gE)/(1-g) = D/(2d)
 // (double_heston.py:64-71, 85-87).  The csqrt formula follows glibc's; products and sums are fused into FMAs
 // wherever possible (an FP64 instruction is the scarce resource); g itself is never formed.
-struct FactorTerms { double Ar, Ai, Bvr, Bvi; };
-
-DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
-                                 const fm::Tables* __restrict__ ltab) {
+// The factor's terms are ADDED to running sums with fused multiply-adds (an FP64 instruction is the scarce
+// resource): aR, aI += A_j without its -2 c_j i arg(.) part, which goes to sli += c_j arg(.);
+// xbr, xbi += B_j v0_j.  Scalars are folded: B_j v0_j = (m (1-E) pl conj(D)) * (|D|^-2 v0/sigma^2), and
+// -2 log|D/(2d)| = log(4 |z| / |D|^2) comes straight from the table-driven log (the 4 is an exponent offset).
+DHJ_HD void heston_factor(const SetConsts& s, int j, double u, double T, const fm::Tables* __restrict__ ltab,
+                          double& aR, double& aI, double& sli, double& xbr, double& xbi) {
   const double kap = s.kappa[j];
   const double bi = -(s.rs[j] * u);                 // Im beta
   const double s2u = s.s2[j] * u;
   // z = beta^2 + sigma^2 u (u+i):  Re = kappa^2 - bi^2 + s2u u,  Im = 2 kappa bi + s2u   (fused: 3 FMAs)
   const double zr = fma(s2u, u, fma(-bi, bi, s.kk[j]));
-  const double zi = fma(kap + kap, bi, s2u);
+  const double zi = fma(s.two_kappa[j], bi, s2u);
   // d = csqrt(z) as glibc does it: h = |z|, t = sqrt((h + |zr|)/2), other = zi/(2t); the roles of t and
   // `other` swap when Re z < 0.  (Re z >= kappa^2 > 0 for |rho| <= 1; the other case is kept for safety.)
   // (square roots as x * rsqrt(x): <= 1 ulp instead of correctly rounded, no zero special case; z = 0 needs
@@ -197,29 +200,27 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
   const double Er = er * cs, Ei = er * sn;
   const double mr = kap - dr, mi = bi - di;         // beta - d
   const double pr = kap + dr, pi_ = bi + di;        // beta + d
-  // D = pl - m*E   (from here on complex products are written with FMAs: nothing below is an operand the
-  // reference rounds separately in the same form, and an FP64 instruction is what the kernel is short of)
+  // D = pl - m*E
   const double Dr = fma(-mr, Er, fma(mi, Ei, pr));
   const double Di = fma(-mr, Ei, fma(-mi, Er, pi_));
   const double nD = fma(Dr, Dr, Di * Di);
   const double inD = fm::rcp(nD);
-  // Q = (1-E) * pl / D = (1-E) * pl * conj(D) / |D|^2
+  // B v0 = m * [(1-E) * pl * conj(D)] * (v0 / (sigma^2 |D|^2))
   const double ar = 1.0 - Er, ai = -Ei;
   const double tr = fma(ar, pr, -(ai * pi_)), ti = fma(ar, pi_, ai * pr);
-  const double Qr = fma(tr, Dr, ti * Di) * inD, Qi = fma(ti, Dr, -(tr * Di)) * inD;
-  // B*v0 = (m * inv_s2) * Q * v0
-  const double msr = mr * s.inv_s2[j], msi = mi * s.inv_s2[j];
-  const double Br = fma(msr, Qr, -(msi * Qi)), Bi = fma(msr, Qi, msi * Qr);
-  // log(D/(2d)) : modulus from |D|^2/(4|d|^2) with |d|^2 = |z| = h ; argument from D*conj(d)
-  // (log of the reciprocal ratio through the table-driven log: 4|z| / |D|^2 is one multiply away)
-  const double lr = -0.5 * fm::log_tab((4.0 * h) * inD, ltab);
+  const double Qr = fma(tr, Dr, ti * Di), Qi = fma(ti, Dr, -(tr * Di));
+  const double Br = fma(mr, Qr, -(mi * Qi)), Bi = fma(mr, Qi, mi * Qr);
+  const double g = inD * s.sv[j];
+  xbr = fma(Br, g, xbr);
+  xbi = fma(Bi, g, xbi);
+  // A = c (m T - 2 log(D/(2d))):  -2 log|D/(2d)| = log(4 |z| / |D|^2), |d|^2 = |z| = h;  argument from D*conj(d)
+  const double L = fm::log_tab(h * inD, ltab, 2);
   const double li = fm::atan2_tab_nz(fma(Di, dr, -(Dr * di)), fma(Dr, dr, Di * di), ltab);
-  FactorTerms f;
-  f.Ar = s.c[j] * fma(mr, T, -2.0 * lr);
-  f.Ai = s.c[j] * fma(mi, T, -2.0 * li);
-  f.Bvr = Br * s.v0[j];
-  f.Bvi = Bi * s.v0[j];
-  return f;
+  const double cT = s.c[j] * T;
+  aR = fma(s.c[j], L, aR);
+  aR = fma(cT, mr, aR);
+  aI = fma(cT, mi, aI);
+  sli = fma(s.c[j], li, sli);
 }
 
 // exponent X of cf_heston * cf_jump = exp(X) at frequency u  (double_heston.py:82-96):
@@ -231,16 +232,11 @@ DHJ_HD FactorTerms heston_factor(const SetConsts& s, int j, double u, double T,
 template <class JumpTrig>
 DHJ_HD void cf_exponent_f(const SetConsts& s, double u, double T, double lamT, const fm::Tables* __restrict__ ltab,
                           JumpTrig jump_trig, double* xr_out, double* xi_out) {
-  double aR = 0.0, aI = (s.drift * u) * T;
-  double b1r = 0.0, b1i = 0.0, b2r = 0.0, b2i = 0.0;
+  double aR = 0.0, aI = (s.drift * u) * T, sli = 0.0, xbr = 0.0, xbi = 0.0;
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const FactorTerms f = heston_factor(s, j, u, T, ltab);
-    aR += f.Ar; aI += f.Ai;
-    if (j == 0) { b1r = f.Bvr; b1i = f.Bvi; } else { b2r = f.Bvr; b2i = f.Bvi; }
-  }
-  double xr = (aR + b1r) + b2r;
-  double xi = (aI + b1i) + b2i;
+  for (int j = 0; j < 2; ++j) heston_factor(s, j, u, T, ltab, aR, aI, sli, xbr, xbi);
+  double xr = aR + xbr;
+  double xi = fma(-2.0, sli, aI) + xbi;
   const double ej = fm::exp_tab_neg(-(s.hsj2 * (u * u)), ltab);
   double cj, sj;
   jump_trig(&cj, &sj);
@@ -291,7 +287,7 @@ DHJ_HD KTerm make_kterm_f(const SetConsts& s, const PassConsts& p, int k, const 
   t.sb = sbv;
   t.t1 = fm::xor_sign(p.eb, k << 31);
   t.t3 = (u * sbv) * p.eb;
-  t.inv1 = fm::rcp(1.0 + u * u);
+  t.inv1 = fm::rcp(fma(u, u, 1.0));
   t.invu = (k == 0) ? 0.0 : fm::rcp(u);
   return t;
 }
