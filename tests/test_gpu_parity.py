@@ -134,7 +134,7 @@ def test_random_sample_vs_oracle(ctx):
     assert err.max() <= PRICE_RTOL
 
 
-@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 100, 129, 300, 512])
+@pytest.mark.parametrize("N", [1, 2, 31, 32, 33, 100, 129, 300, 512, 1000, 2048])
 def test_ragged_n(ctx, N):
     rng = np.random.default_rng(N)
     params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(7, 13))
