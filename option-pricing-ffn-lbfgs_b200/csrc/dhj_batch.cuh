@@ -164,7 +164,9 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
   double a1 = 0.0, a2 = 0.0, a3 = 0.0, g0_keep = 0.0;
   double cj = 1.0, sj = 0.0, cs = 1.0, sn = 0.0;
   int blk = 0;
-#pragma unroll 1
+  // two blocks of k per trip in the register-rich pricing kernel (the `exact` test and the loop overhead are
+  // shared; four copies overflow the instruction cache: 13.29 / 13.06 / 14.73 ms for 1 / 2 / 4)
+#pragma unroll(PARK ? 1 : 2)
   for (int k0 = 0; k0 < n_cos; k0 += 32, ++blk) {
     const int k = k0 + lane;
     const bool exact = (blk % kReseed) == 0;               // uniform
