@@ -58,8 +58,11 @@ mats = np.repeat(MATURITIES, 5)
 from dhj.shard import shard_bounds  # noqa: E402
 model = ctx.price_grid(params, spots, STRIKES.astype(float), MATURITIES, 0.03, scale_by_spot=True).reshape(n_markets, 15)
 market = model * (1 + 0.02 * rng.standard_normal((n_markets, 15)))                         # generator's 2 % noise
+# warm-up at full size: device / pinned buffers of the final shapes, NCCL communicator (its first collective costs ~1 s)
 np.random.seed(1)
-dhj.calibrate_many(spots[:64], 0.03, strikes[:64], mats, np.ones(15), market[:64], maxiter=5)   # warm-up
+dhj.calibrate_many_sharded(spots, 0.03, strikes, mats, np.ones(15), market, maxiter=2, multi_start=3, device=device)
+if world > 1:
+    dist.barrier()
 np.random.seed(1)
 launches0 = ctx.launch_count
 t0 = time.perf_counter()
