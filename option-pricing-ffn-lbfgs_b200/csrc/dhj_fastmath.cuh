@@ -8,8 +8,13 @@
 // functions below are straight-line code: FMA polynomials with coefficients in __constant__ memory
 // (operands come straight from the constant bank), magic-number rounding, integer exponent tricks.
 //
-// Accuracy (scripts/check_fastmath.py, against mpmath): sincos <= 1.5 ulp for |x| <= 1e5, exp <= 1 ulp,
-// log_ratio abs error <= 2e-16 * max(1, |log|), atan2 <= 2 ulp, rcp/div/sqrt/rsqrt <= 1 ulp.
+// The characteristic function uses table-driven variants (log_tab, exp_tab, atan2_tab: 2.6 KB of tables that the
+// kernels copy into shared memory) with shorter polynomials; the highest polynomial coefficients are rounded to
+// a high word so that they fit an FP64 instruction's 32-bit immediate (scripts/gen_poly.py imm).
+//
+// Accuracy (tests/test_fastmath.py, against mpmath): sincos <= 1.5 ulp for |x| <= 1e5, exp / exp_tab <= 1 ulp,
+// log_ratio / log_tab abs error <= 2.3e-16 * max(1, |log|), atan2 / atan2_tab <= 2 ulp, rcp/div/sqrt <= 1 ulp,
+// rsqrt <= 1.5 ulp.
 // NaN propagates; +-inf and out-of-range arguments give the IEEE limits where the path can produce
 // them (exp), otherwise NaN.
 //
@@ -126,7 +131,7 @@ struct ScalarConsts {
   double Ln2Hi64;      // (ln 2)/64, high 32 bits and the rest
   double Ln2Lo64;
   double AtanMagic;    // 1.5 * 2^46: (t + magic) - magic = t rounded to a multiple of 1/64, low word = 64 t
-  double AtC1, AtC2, AtC3;   // atan t = t + t z (C1 + C2 z + C3 z^2), z = t^2
+  double AtC1, AtC2;   // atan t = t + t z (C1 + C2 z + C3 z^2), z = t^2; C3 = -1/7 is an immediate (atan2_tab_impl)
 };
 DHJ_CONSTANT ScalarConsts kS = {
   6.36619772367581382433e-01,
@@ -148,7 +153,7 @@ DHJ_CONSTANT ScalarConsts kS = {
   6.93147180369123816490e-01 / 64.0,
   1.90821492927058770002e-10 / 64.0,
   1.5 * 70368744177664.0,
-  -1.0 / 3.0, 0.2, -0.14285719394683837891};     // AtC3: -1/7 as a high word (its term is below 2^-41)
+  -1.0 / 3.0, 0.2};
 
 // ---- sincos ----------------------------------------------------------------------------------------
 // sin r = r + r z S(z), cos r = 1 - z/2 + z^2 C(z), z = r^2 <= (pi/4)^2: minimax fits (scripts/gen_poly.py imm:
