@@ -261,14 +261,31 @@ int run_price_host(dhj_ctx* ctx, SliceView v, int max_slice, const double* param
   if (P == 0 || M == 0) return DHJ_OK;
   const size_t in_row = (size_t)kNumParams + (s0_stride ? 1 : 0) + (strike_stride ? (size_t)M : 0);
   const size_t row_doubles = in_row + (size_t)M;
-  int64_t chunk = (int64_t)std::max<size_t>(256, std::min<size_t>(131072, ((size_t)1 << 23) / row_doubles));
-  chunk = std::min<int64_t>(chunk, P);
+  const int64_t chunk = (int64_t)std::max<size_t>(256, std::min<size_t>(131072, ((size_t)1 << 23) / row_doubles));
   const bool pin_in = is_pinned_host(params) && (!s0_stride || is_pinned_host(S0)) &&
                       (!strike_stride || is_pinned_host(strike));
   const bool pin_out = is_pinned_host(out);
+  // Chunk schedule: the first chunk's upload and the last chunk's download cannot overlap any kernel, so with
+  // pinned buffers the schedule ramps up from chunk/8 and down to chunk/8 again (exposed transfer 0.54 -> 0.07 ms
+  // on the 1 Mi-set grid: 13.87 -> 13.23 ms).  Pageable buffers keep uniform chunks: their staging copies make
+  // the host the bottleneck while the chunks are small (14.9 vs 15.2 ms).
+  std::vector<int64_t> sizes;
+  {
+    std::vector<int64_t> head, tail;
+    int64_t left = P;
+    if (pin_in && pin_out)
+      for (int64_t s = chunk / 8; s < chunk && left > 2 * s + chunk; s *= 2) {
+        head.push_back(s); tail.push_back(s);
+        left -= 2 * s;
+      }
+    sizes = head;
+    for (; left > 0; left -= chunk) sizes.push_back(std::min(chunk, left));
+    sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
+  }
   int slot_i = 0;
-  for (int64_t lo = 0; lo < P; lo += chunk, slot_i ^= 1) {
-    const int64_t n = std::min<int64_t>(chunk, P - lo);
+  int64_t lo = 0;
+  for (size_t ci = 0; ci < sizes.size(); lo += sizes[ci], ++ci, slot_i ^= 1) {
+    const int64_t n = sizes[ci];
     Slot& sl = ctx->slots[slot_i];
     // the slot's previous chunk must have left its buffers
     DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));
