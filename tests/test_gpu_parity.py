@@ -292,7 +292,8 @@ def test_host_path_chunking_and_memory_kinds(ctx):
     on chunk boundaries, on per-set strikes / spots being present, or on the caller's memory being pinned."""
     import torch
     rng = np.random.default_rng(12)
-    P = 300_001                                                  # three chunks, the last one ragged
+    P = 300_001              # pageable: three uniform chunks, the last one ragged; pinned: ramped schedule
+                             # 16 384, 32 768, 131 072, 70 625, 32 768, 16 384 (dhj_abi.cu run_price_host)
     params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(P, 13))
     spots = rng.uniform(80, 120, size=P)
     Ks, Ts = O.GENERATOR_STRIKES_REL, O.GENERATOR_MATURITIES
@@ -306,7 +307,7 @@ def test_host_path_chunking_and_memory_kinds(ctx):
     lst = ctx.price_list(params, spots, K, T, np.ones(15), 0.03)
     assert np.array_equal(lst.reshape(P, 3, 5), pageable)
     # rows around the chunk boundaries against single-set calls
-    for p in (0, 131071, 131072, 262143, 262144, P - 1):
+    for p in (0, 16383, 16384, 49151, 49152, 131071, 131072, 180223, 180224, 262143, 262144, P - 16385, P - 1):
         one = ctx.price_grid(params[p], spots[p], Ks, Ts, 0.03, scale_by_spot=True)[0]
         assert np.array_equal(one, pageable[p]), p
     sel = rng.choice(P, size=300, replace=False)
