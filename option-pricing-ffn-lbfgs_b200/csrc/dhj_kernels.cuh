@@ -234,8 +234,10 @@ __global__ void k_fd_expand(const double* __restrict__ x, const int* __restrict_
   row_index[unit] = market_index ? market_index[c] : 0;
 }
 
+// (options are visited in slice order, pos[i], exactly as k_loss_batch does: the two paths give the same bits)
 __global__ void k_loss_reduce(const double* __restrict__ prices, const double* __restrict__ xv,
-                              const int* __restrict__ row_index, const double* __restrict__ market, int M,
+                              const int* __restrict__ row_index, const double* __restrict__ market,
+                              const int* __restrict__ pos, int M,
                               long long n_x, int fd, double h, const double* __restrict__ x,
                               double* __restrict__ f_all, double* __restrict__ fg) {
   const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,7 +250,8 @@ __global__ void k_loss_reduce(const double* __restrict__ prices, const double* _
     const double* mk = market + (long long)row_index[unit] * M;
     double sq = 0.0;
     bool bad = false;
-    for (int o = 0; o < M; ++o) {
+    for (int i = 0; i < M; ++i) {
+      const int o = pos[i];
       const double price = pr[o];
       if (!(price > 0.0) || isinf(price)) bad = true;
       const double rel = (price - mk[o]) / mk[o];

@@ -155,6 +155,26 @@ def test_empty_and_errors(ctx):
     assert np.isnan(ctx.price_list(p, 100.0, [100.0], [1.0], [1], 0.05)).all()
 
 
+def test_loss_paths_agree_bitwise(ctx, golden):
+    """Small batches run the fused loss kernel, large ones expand -> pricing kernel -> reduce (dhj_abi.cu run_loss):
+    the same states must give the same bits either way, for losses and FD gradients."""
+    g = golden("loss_cases.npz")
+    mk = ctx.market(float(g["c1_spot"]), float(g["c1_r"]), g["c1_strike"], g["c1_maturity"], g["c1_is_call"],
+                    g["c1_market"])
+    rng = np.random.default_rng(5)
+    x = g["c1_x"][0] + 0.05 * rng.standard_normal((3000, 13))
+    x[7, 3] = 4.0                                                  # Feller penalty active
+    x[11, 0] = np.nan                                              # sentinel
+    f_big, g_big = mk.loss_fd(x, 1e-8)                             # 42 000 evaluations: split path
+    f_small, g_small = mk.loss_fd(x[:64], 1e-8)                    # 896 evaluations: fused kernel
+    assert np.array_equal(f_big[:64], f_small, equal_nan=True) and np.array_equal(g_big[:64], g_small, equal_nan=True)
+    l_big = mk.loss_batch(np.tile(x, (7, 1)))                      # 21 000 evaluations: split path
+    l_small = mk.loss_batch(x[:500])
+    assert np.array_equal(l_big[:500], l_small, equal_nan=True) and np.array_equal(l_small[:64], f_small, equal_nan=True)
+    assert f_small[11] == 1e10 and f_small[7] > 1.0
+    mk.close()
+
+
 @pytest.mark.parametrize("tag", ["c1", "ragged"])
 def test_loss_golden(ctx, golden, tag):
     g = golden("loss_cases.npz")
