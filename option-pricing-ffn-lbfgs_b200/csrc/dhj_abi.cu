@@ -590,9 +590,9 @@ static int run_loss(dhj_ctx* ctx, const dhj_market* mk, const double* x, const i
   }
   const SliceView& v = mk->view;
   // Large batches go through the pricing kernel (expand -> k_price_batch -> reduce): compiled for 128 registers it
-  // prices 20 % faster than the fused loss kernel, which pays for two extra small launches from ~16 k loss
+  // prices 20 % faster than the fused loss kernel, which pays for two extra small launches from ~8 k loss
   // evaluations on (a 30 000-state FD round: 6.2 -> 5.4 ms).  Both paths produce the same bits.
-  constexpr int64_t kSplitUnits = 16384;
+  constexpr int64_t kSplitUnits = 8192;
   if (mk->book.max_slice <= kBatchMaxStrikes && v.n_slices <= kBatchItems && n_units < kSplitUnits) {
     // fused path: one launch
     if (fd) {
