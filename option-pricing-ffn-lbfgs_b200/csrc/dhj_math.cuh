@@ -352,7 +352,7 @@ DHJ_HD void segment_sums(const Pair* __restrict__ PQ, const Pair* __restrict__ R
   const double two_c = cth + cth;
   pq = PQ[1];
   apq = fma(pq.x, c1, apq); apq = fma(pq.y, s1, apq); ar = fma(rr.y, s1, ar);
-#pragma unroll 2
+#pragma unroll
   for (int i = 2; i < SEG; i += 2) {
     double c2 = fma(two_c, c1, -c), s2 = fma(two_c, s1, -s);          // (k0 + i) theta
     c = c1; s = s1; c1 = c2; s1 = s2;
