@@ -268,7 +268,11 @@ int run_price_host(dhj_ctx* ctx, SliceView v, int max_slice, const double* param
   if (P == 0 || M == 0) return DHJ_OK;
   const size_t in_row = (size_t)kNumParams + (s0_stride ? 1 : 0) + (strike_stride ? (size_t)M : 0);
   const size_t row_doubles = in_row + (size_t)M;
-  const int64_t chunk = (int64_t)std::max<size_t>(256, std::min<size_t>(131072, ((size_t)1 << 23) / row_doubles));
+  int64_t chunk = (int64_t)std::max<size_t>(256, std::min<size_t>(131072, ((size_t)1 << 23) / row_doubles));
+  // a call that moves more than 16 MB is cut into at least 8 chunks so that transfers overlap kernels even when
+  // one set is large (the 200 x 20 surface: 32 KB of prices per set, 1 024 sets -> 8 chunks of 128)
+  if ((size_t)P * row_doubles * sizeof(double) > ((size_t)16 << 20))
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>(32, (P + 7) / 8));
   const bool pin_in = is_pinned_host(params) && (!s0_stride || is_pinned_host(S0)) &&
                       (!strike_stride || is_pinned_host(strike));
   const bool pin_out = is_pinned_host(out);
@@ -280,7 +284,7 @@ int run_price_host(dhj_ctx* ctx, SliceView v, int max_slice, const double* param
   {
     std::vector<int64_t> head, tail;
     int64_t left = P;
-    if (pin_in && pin_out)
+    if (pin_in && pin_out && chunk >= 1024)
       for (int64_t s = chunk / 8; s < chunk && left > 2 * s + chunk; s *= 2) {
         head.push_back(s); tail.push_back(s);
         left -= 2 * s;
