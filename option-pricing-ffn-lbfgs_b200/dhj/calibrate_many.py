@@ -23,7 +23,8 @@ _LITERATURE = np.array([0.04, 2.5, 0.04, 0.3, -0.7, 0.04, 0.5, 0.04, 0.2, -0.5, 
 def inverse_transform(p: np.ndarray) -> np.ndarray:
     """Model parameters -> unconstrained x (lbfgs_calibrator.py:89-109), rows of 13."""
     p = np.asarray(p, dtype=np.float64)
-    x = np.log(np.where(np.arange(13) == 11, 1.0, p))
+    # columns 4, 9 (rho < 0) and 11 (mu_j) are overwritten below: keep them out of the log
+    x = np.log(np.where(np.isin(np.arange(13), (4, 9, 11)), 1.0, p))
     x[..., 4] = np.arctanh(np.clip(p[..., 4], -0.999, 0.999))
     x[..., 9] = np.arctanh(np.clip(p[..., 9], -0.999, 0.999))
     x[..., 11] = p[..., 11]
