@@ -2,8 +2,8 @@
 // (the 15-option grid of C2 / C4 / the generator / the calibrator's market).
 //
 // Decomposition: ONE LANE PER COSINE INDEX k, a block of 128 threads walks a batch of
-// 32 items (item = one (parameter set, maturity slice)):
-//   phase 1  thread t < 32 prepares item t ALONE: parameters (optionally exp/tanh transform), per-set
+// 28 items (item = one (parameter set, maturity slice)):
+//   phase 1  thread t < 28 prepares item t ALONE: parameters (optionally exp/tanh transform), per-set
 //            constants, truncation range, pass constants, the slice's strikes (K, log(K/S0), exp(.),
 //            binding flags) -> shared memory.  The prologue is therefore executed once per item by one
 //            lane instead of redundantly by every lane of a warp (it was ~10 % of the warp-per-item
@@ -52,10 +52,11 @@ struct ItemRec {
   long long out_row;               // p * M
 };
 
-// one warp's k-block of strike-independent coefficients P, Q, R.  Between two blocks of k the same slots park the
-// lanes' rotation state (P, Q = cos / sin(u_k mu); R, X = the segment start's cos / sin), so that it does not
-// occupy registers while the characteristic function is evaluated.  A1, A2, A3 accumulate each lane's share of
-// the strike-independent sums over all blocks of a pass (reduced once per pass, not once per block).
+// one warp's k-block of strike-independent coefficients P, Q, R.  In the 72-register loss kernel (PARK) the same
+// slots park the lanes' rotation state between two blocks of k (PQ = cos / sin(u_k mu); R, X = the segment start's
+// cos / sin), so that it does not occupy registers while the characteristic function is evaluated, and A1, A2, A3
+// accumulate each lane's share of the strike-independent sums over all blocks of a pass (reduced once per pass,
+// not once per block); the 128-register pricing kernel keeps all of that in registers.
 // Layout: PQ[k] = (P_k, Q_k) and R[k], for 128-bit loads in the contraction (one for P and Q, one for two consecutive
 // R); the batch kernel's four 8-term segments are read concurrently by different lanes, so each segment is shifted
 // by one 16-byte slot (PQ) / two doubles (R) to land in different banks.

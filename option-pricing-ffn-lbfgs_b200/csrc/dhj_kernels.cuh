@@ -1,11 +1,12 @@
 // dhj_kernels.cuh — the CUDA kernels of libdhj.so (sm_100a).
 //
-//   k_price_batch  slices of <= 8 strikes: thread per cosine index, 32 items per block batch   (K1 / K3 of SURVEY §2)
+//   k_price_batch  slices of <= 8 strikes: warp per item, lane per cosine index, 28 items per block   (K1 / K3 of SURVEY §2)
 //   k_price_dense  many strikes per slice: block per item, lane per strike
 //   k_loss_batch   K2: exp/tanh transform + prices of every market option + relative-MSE + Feller penalty +
 //                  1e10 sentinel; in FD mode the 14 stencil points of an optimiser state are 14 units and the
 //                  thread that finishes the last one assembles scipy's gradient — ONE launch per optimiser step
-//   k_fd_expand / k_loss_reduce  general fallback of K2 around k_price_dense
+//   k_fd_expand / k_loss_reduce  K2 around the pricing kernels: markets with > 8 strikes per maturity, and any
+//                  batch of >= 8 192 loss evaluations (the 128-register k_price_batch outruns the fused kernel)
 //   k_cf / k_truncation_range / k_chi_psi  the remaining public methods of DoubleHeston
 //   k_fp64_peak    DFMA-chain probe for the FP64 roofline denominator
 #pragma once
@@ -28,7 +29,7 @@ struct PriceArgs {
   double* out;               // [P][M]
 };
 
-// Throughput variant of k_price for slices of <= 8 strikes: see dhj_batch.cuh.
+// Slices of <= 8 strikes: see dhj_batch.cuh.
 __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(SliceView v, PriceArgs a) {
   __shared__ BatchSmem sm;
   const int tid = threadIdx.x;
