@@ -156,6 +156,38 @@ def test_generator_draws_match_numpy_stream(dropins):
         assert np.random.random() == (np.random.set_state(end), np.random.random())[1]
 
 
+def test_flat_dataset_sinks_and_lazy_view(dropins, tmp_path):
+    """SURVEY §8f N1 on the host side: .npz / directory-of-.npy sinks and the lazy CalibrationResult view
+    (no pricing involved: the arrays are made up)."""
+    _, cal, gen = dropins
+    n = 12
+    rng = np.random.default_rng(3)
+    data = {"param_names": list(gen.PARAM_RANGES), "params": rng.uniform(0.01, 1.0, (n, 13)),
+            "spots": 100.0 + rng.standard_normal(n), "strikes": rng.uniform(80, 120, (n, 15)),
+            "maturities": np.repeat(gen.MATURITIES, 5), "model_prices": rng.uniform(1, 20, (n, 15)),
+            "market_prices": rng.uniform(1, 20, (n, 15)), "losses": rng.uniform(0, 1e-3, n)}
+    gen._save_arrays(data, tmp_path / "flat")
+    gen._save_arrays(data, str(tmp_path / "flat.npz"))
+    for ds, mapped in ((gen.SyntheticCalibrationSet.load(tmp_path / "flat"), True),
+                       (gen.SyntheticCalibrationSet.load(str(tmp_path / "flat.npz")), False),
+                       (gen.SyntheticCalibrationSet(data), False)):
+        assert len(ds) == n and isinstance(ds.data["params"], np.memmap) == mapped
+        r = ds[5]
+        assert isinstance(r, cal.CalibrationResult) and r.date == gen._trading_dates(6)[5]
+        assert r.spot == data["spots"][5] and r.risk_free == gen.RISK_FREE and r.final_loss == data["losses"][5]
+        assert list(r.parameters) == list(gen.PARAM_RANGES) and r.parameters["kappa1"] == data["params"][5, 1]
+        assert np.array_equal(r.market_prices, data["market_prices"][5]) and len(r.market_options) == 15
+        assert r.market_options[7] == {"strike": data["strikes"][5, 7], "maturity": 0.5,
+                                       "price": data["market_prices"][5, 7], "option_type": "call"}
+        assert r.calibration_time is None and r.iterations is None and r.success is True
+        assert ds[-1].date == gen._trading_dates(n)[-1]
+        sub = ds[3:9]
+        assert len(sub) == 6 and sub[2].date == r.date and sub[2].spot == r.spot       # dates follow the slice
+        assert [x.spot for x in ds] == list(data["spots"])
+        with pytest.raises(IndexError):
+            ds[n]
+
+
 def test_lockstep_evaluator_batches_requests(dropins):
     """The multi-start driver answers one request per running optimiser with ONE launch, also when
     optimisers retire at different times."""
