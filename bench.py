@@ -408,10 +408,44 @@ def run_b200_arm(args, wl):
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if args.workload == "c2":
+            line["calibration"] = time_readme_calibration(ctx)
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_readme_calibration(ctx, repeats=5):
+    """Second half of BASELINE.json's metric: seconds per 15-option calibration, the README configuration (C1):
+    DoubleHestonJumpCalibrator(...).calibrate(maxiter=300, multi_start=3) through the drop-in class on the
+    reference suite's market (tests/test_suite.py:274-302).  Reference: 425 s in the build container, 117.8 s
+    published (README.md:173)."""
+    for sub in ("models", "calibration"):
+        sys.path.insert(0, os.path.join(ROOT, "option-pricing-ffn-lbfgs_b200", "src", sub))
+    from lbfgs_calibrator import DoubleHestonJumpCalibrator
+    from dhj import default_context
+    cal_ctx = default_context()                                              # the context the drop-in classes use
+    true_p = np.array([0.04, 2.0, 0.04, 0.3, -0.5, 0.04, 1.5, 0.04, 0.2, -0.3, 0.1, 0.0, 0.1])
+    K = np.tile([90.0, 95.0, 100.0, 105.0, 110.0], 3)
+    T = np.repeat([0.25, 0.5, 1.0], 5)
+    mkt = ctx.price_list(true_p, 100.0, K, T, np.ones(15), 0.05)[0]
+    opts = [{"strike": K[j], "maturity": T[j], "price": mkt[j], "option_type": "call"} for j in range(15)]
+    cal = DoubleHestonJumpCalibrator(100.0, 0.05, opts)
+    cal.calibrate(maxiter=3, multi_start=1)                                   # warm-up
+    times, res = [], None
+    for _ in range(repeats):
+        np.random.seed(0)
+        launches0 = cal_ctx.launch_count
+        t0 = time.perf_counter()
+        res = cal.calibrate(maxiter=300, multi_start=3)
+        times.append(time.perf_counter() - t0)
+        launches = cal_ctx.launch_count - launches0
+    return {"metric": "s per 15-option calibration (maxiter=300, multi_start=3)", "value": float(np.median(times)),
+            "min": float(min(times)), "unit": "s", "higher_is_better": False, "repeats": repeats,
+            "final_loss": float(res.final_loss), "iterations": int(res.iterations), "gpu_launches": int(launches),
+            "api": "DoubleHestonJumpCalibrator.calibrate -> dhj_loss_fd (one launch per optimiser round)",
+            "reference_seconds": {"build_container": 425.0, "published_m1": 117.8}}
 
 
 def main():
