@@ -199,7 +199,7 @@ bool is_pinned_host(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
-// k_price_batch handles slices of <= 8 strikes (one thread per k, 32 items per block batch); k_price the rest
+// k_price_batch handles slices of <= 8 strikes (warp per item, lane per k, 28 items per block); k_price_dense the rest
 int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_slice, cudaStream_t st);
 
 int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_slice, cudaStream_t st) {
@@ -613,7 +613,7 @@ static int run_loss(dhj_ctx* ctx, const dhj_market* mk, const double* x, const i
     a.f_all = (double*)ctx->d_f.p; a.fg = fd ? (double*)ctx->d_fg.p : nullptr;
     a.counters = fd ? (unsigned int*)ctx->d_counters.p : nullptr;
     // whole units per block batch; few units (one calibration) -> one unit per block so that every unit
-    // runs on its own SM (latency), many units -> full 32-item batches (throughput)
+    // runs on its own SM (latency), many units -> full batches of kBatchItems items (throughput)
     const int upb_max = std::max(1, kBatchItems / v.n_slices);
     const long long resident = (long long)ctx->sm_count * ctx->loss_blocks_per_sm;
     a.units_per_batch = (int)std::max<long long>(1, std::min<long long>(upb_max, n_units / resident));

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_DENSE_MINB) k_price_dense(S
 
 // Fused loss kernel on the batch engine (slices of <= 8 strikes, <= 32 slices): a "unit" is one loss evaluation
 // (one x; in FD mode one of the 14 stencil points of an optimiser state); a block batch holds
-// `units_per_batch` whole units (= units_per_batch * n_slices <= 32 items), prices them as k_price_batch does,
+// `units_per_batch` whole units (= units_per_batch * n_slices <= kBatchItems items), prices them as k_price_batch does,
 // then one thread per unit forms mean(rel^2) + Feller / the 1e10 sentinel, and the thread that completes a
 // state's 14th point assembles scipy's forward-difference gradient.
 struct LossBatchArgs {
