@@ -199,13 +199,13 @@ bool is_pinned_host(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
-// k_price_batch handles slices of <= 8 strikes (warp per item, lane per k, 28 items per block); k_price_dense the rest
+// k_price_batch handles slices of <= 8 strikes (warp per item, lane per k, 32 items per block); k_price_dense the rest
 int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_slice, cudaStream_t st);
 
 int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_slice, cudaStream_t st) {
   const long long items = a.P * (long long)v.n_slices;
   if (max_slice <= kBatchMaxStrikes) {
-    const long long batches = (items + kBatchItems - 1) / kBatchItems;
+    const long long batches = (items + kPriceItems - 1) / kPriceItems;
     // one block per batch: the hardware block scheduler balances the SMs dynamically (a persistent grid with a
     // static batch -> block map measured ~3 % slower: the slowest SM sets the time)
     const long long cap = 2147483647LL;

@@ -2,8 +2,8 @@
 // (the 15-option grid of C2 / C4 / the generator / the calibrator's market).
 //
 // Decomposition: ONE LANE PER COSINE INDEX k, a block of 128 threads walks a batch of
-// 28 items (item = one (parameter set, maturity slice)):
-//   phase 1  thread t < 28 prepares item t ALONE: parameters (optionally exp/tanh transform), per-set
+// 32 items (28 in the loss kernel; item = one (parameter set, maturity slice)):
+//   phase 1  thread t < 32 prepares item t ALONE: parameters (optionally exp/tanh transform), per-set
 //            constants, truncation range, pass constants, the slice's strikes (K, log(K/S0), exp(.),
 //            binding flags) -> shared memory.  The prologue is therefore executed once per item by one
 //            lane instead of redundantly by every lane of a warp (it was ~10 % of the warp-per-item
@@ -23,10 +23,16 @@ namespace dhj {
 
 constexpr int kBatchThreads = 128;
 constexpr int kBatchWarps = kBatchThreads / 32;
+// items per block batch: 28 in the loss kernel (its 7 blocks/SM leave 32 KB of shared memory per block), 32 in the
+// pricing kernel (4 blocks/SM: shared memory is not the limit, and phase 1 then fills its warp)
 #ifndef DHJ_BATCH_ITEMS
 #define DHJ_BATCH_ITEMS 28
 #endif
+#ifndef DHJ_PRICE_ITEMS
+#define DHJ_PRICE_ITEMS 32
+#endif
 constexpr int kBatchItems = DHJ_BATCH_ITEMS;
+constexpr int kPriceItems = DHJ_PRICE_ITEMS;
 constexpr int kBatchMaxStrikes = 8;
 // resident blocks per SM the kernels are compiled for (register budget = 65 536 / (128 * MINB)).  Measured on C2
 // (profiles/README.md): 7 blocks at 72 registers 14.36 ms, 6 at 80 14.40, 5 at 96 14.51, 4 at 122 14.03, 3 at 140
@@ -73,12 +79,15 @@ struct ExtraPass {
   double cth, sth, c32, s32, cmu, smu;
 };
 
-struct BatchSmem {
-  ItemRec items[kBatchItems];
+template <int ITEMS>
+struct BatchSmemT {
+  ItemRec items[ITEMS];
   ExtraPass extra[kBatchWarps];
   CoefStage stage[kBatchWarps];
   fm::Tables ltab;                 // fm::log_tab / exp_tab / atan2_tab tables (per-lane index: shared memory, not the constant bank)
 };
+using BatchSmem = BatchSmemT<kBatchItems>;        // loss kernel
+using PriceSmem = BatchSmemT<kPriceItems>;        // pricing kernel
 
 struct PriceArgs;                  // dhj_kernels.cuh
 
@@ -229,8 +238,8 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
 // phase 2 for a batch of `cnt_items` prepared items: warp w prices items w, w + 4, ... on its own — no block
 // barrier, no partial sums in shared memory; sink(i, j, item, price) receives each price from lane 4 j.
 // Strikes with their own (a, b) get an extra pass each (rare), set up by lane 0 in the warp's ExtraPass.
-template <bool PARK, class Sink>
-__device__ __forceinline__ void run_batch(BatchSmem& sm, const SliceView& v, int cnt_items, int tid, Sink sink) {
+template <bool PARK, class Smem, class Sink>
+__device__ __forceinline__ void run_batch(Smem& sm, const SliceView& v, int cnt_items, int tid, Sink sink) {
   // the shuffle tells ptxas that the warp index is warp-uniform: the item loop and everything addressed through it
   // then run on the uniform datapath (constants via LDCU into uniform registers, address arithmetic off the
   // vector pipe)

@@ -1,6 +1,6 @@
 // dhj_kernels.cuh — the CUDA kernels of libdhj.so (sm_100a).
 //
-//   k_price_batch  slices of <= 8 strikes: warp per item, lane per cosine index, 28 items per block   (K1 / K3 of SURVEY §2)
+//   k_price_batch  slices of <= 8 strikes: warp per item, lane per cosine index, 32 items per block   (K1 / K3 of SURVEY §2)
 //   k_price_dense  many strikes per slice: block per item, lane per strike
 //   k_loss_batch   K2: exp/tanh transform + prices of every market option + relative-MSE + Feller penalty +
 //                  1e10 sentinel; in FD mode the 14 stencil points of an optimiser state are 14 units and the
@@ -31,14 +31,14 @@ struct PriceArgs {
 
 // Slices of <= 8 strikes: see dhj_batch.cuh.
 __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(SliceView v, PriceArgs a) {
-  __shared__ BatchSmem sm;
+  __shared__ PriceSmem sm;
   const int tid = threadIdx.x;
   load_log_table(&sm.ltab, tid);
   const long long n_items = a.P * (long long)v.n_slices;
-  const long long n_batches = (n_items + kBatchItems - 1) / kBatchItems;
+  const long long n_batches = (n_items + kPriceItems - 1) / kPriceItems;
   for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-    const long long base = batch * kBatchItems;
-    const int cnt_items = (int)min((long long)kBatchItems, n_items - base);
+    const long long base = batch * kPriceItems;
+    const int cnt_items = (int)min((long long)kPriceItems, n_items - base);
     // ---- phase 1: one thread per item ----------------------------------------------------------
     if (tid < cnt_items) {
       const long long item = base + tid;
