@@ -202,6 +202,30 @@ def test_calibrate_many(mods, golden):
     assert res['rounds'] <= 21 * 301
 
 
+def test_calibrate_many_pipelines_agree(mods):
+    """Two host pipelines (two contexts, two threads) give the same bits as one lock-step loop: every optimiser
+    state is independent of how the states are grouped into launches."""
+    import dhj
+    from oracle import cos_oracle as O
+    rng = np.random.default_rng(17)
+    n = 2400
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(n, 13))
+    spots = rng.uniform(90, 110, size=n)
+    K = np.tile(O.GENERATOR_STRIKES_REL[None, :] * spots[:, None] / 100.0, (1, 3))
+    T = np.repeat(O.GENERATOR_MATURITIES, 5)
+    market = dhj.default_context().price_list(params, spots, K, T, np.ones(15), 0.03) * \
+        (1 + 0.01 * rng.standard_normal((n, 15)))
+    out = []
+    for pipes in (1, 2):
+        np.random.seed(5)
+        t0 = time.perf_counter()
+        out.append(dhj.calibrate_many(spots, 0.03, K, T, np.ones(15), market, maxiter=40, multi_start=3,
+                                      pipelines=pipes))
+        print(f"calibrate_many, {n} markets, maxiter 40, pipelines={pipes}: {time.perf_counter() - t0:.3f} s")
+    for key in ('x', 'final_loss', 'iterations', 'status', 'best_start', 'model_prices'):
+        assert np.array_equal(out[0][key], out[1][key], equal_nan=True), key
+
+
 def test_puts_parity_and_jump_limit(mods):
     """The checks the reference's docs promise but its suite does not run (docs/METHODOLOGY.md:150-156):
     put-call parity across the grid, the lambda -> 0 limit, and price bounds."""
