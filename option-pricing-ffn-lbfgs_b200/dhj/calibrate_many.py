@@ -94,8 +94,8 @@ def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, 
 
     With `pipelines=2` and enough markets the set is cut in two halves that run their lock-step loops in two
     threads on two contexts (streams) of the same GPU: while one half's loss launch runs, the other half's host
-    optimiser (ask / tell, C++ under a released GIL) works — the host share of a round (~20 %) disappears from the
-    wall time.  Every optimiser state is independent of the others, so the result does not depend on the split.
+    optimiser (ask / tell, C++ under a released GIL) works — part of the host share of a round (~20 %) disappears
+    from the wall time (10 000 markets: 0.80 -> 0.73 s).  Every optimiser state is independent of the others, so the result does not depend on the split.
     """
     t0 = time.time()
     n_all = np.asarray(spots).size
