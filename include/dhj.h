@@ -138,7 +138,10 @@ DHJ_API int dhj_chi_psi(dhj_ctx* ctx, const int32_t* k, int32_t n, double c, dou
  * with at most maxls = 20 trials, stop on max|g| <= pgtol or (f_old - f) <= ftol * max(|f_old|,|f|,1), iteration
  * and evaluation limits), restated so that one `ask` / one GPU launch (dhj_loss_fd) / one `tell` advances
  * every calibration at once.  Host-only code.  status[i]: 0 converged (pgtol), 1 converged (ftol),
- * 2 iteration limit, 3 evaluation limit, 4 abnormal (line search failed). */
+ * 2 iteration limit, 3 evaluation limit, 4 abnormal (line search failed).
+ * `maxfun` counts (f, g) requests (one dhj_loss_fd row each).  The reference runs scipy with jac=None, where a
+ * request costs 14 loss evaluations against scipy's default maxfun = 15000 (lbfgs_calibrator.py:259-269 sets no
+ * maxfun): pass 15000 / 14 = 1071 for the reference's limit. */
 typedef struct dhj_lbfgs dhj_lbfgs;
 DHJ_API int dhj_lbfgs_create(int64_t n_states, int32_t dim, int32_t m, int32_t maxiter, int32_t maxfun, int32_t maxls,
                              double ftol, double pgtol, const double* x0, dhj_lbfgs** out);
@@ -163,6 +166,34 @@ DHJ_API int dhj_generator_draws(const uint32_t* mt_key, int32_t mt_pos, int32_t 
                                 double spot0, double ret_mean, double ret_sd, double noise_sd, int32_t n_noise,
                                 double* params, double* spots, double* noise, uint32_t* out_key, int32_t* out_pos,
                                 int32_t* out_has_gauss, double* out_cached_gauss);
+
+/* ---- synthetic dataset sweep on the device (SURVEY "K3", BASELINE config 4) -------------------
+ * Per-sample semantics of generate_synthetic_calibrations (/root/reference/src/data/synthetic_generator.py:98-157):
+ * 13 uniform parameters in [lo, hi) (:100-102), AR(1) smoothing with `persistence` (:105-109), spot walk
+ * spot * (1 + N(ret_mean, ret_sd)) from spot0 (:112-116), the nT x nK grid of calls at K = strikes_rel * spot / 100
+ * priced with rate r and COS size N (:123-138), market = model + N(0, noise_sd) * model (:141-142) and
+ * loss = mean(((model - market) / market)^2) (:154-157) — for samples [first, first + n) of the COUNTER STREAM
+ * `seed`: every draw is a Philox4x32-10 function of (seed, sample index, slot), so any index range can be produced
+ * on any GPU in any order and a sharded dataset does not depend on the number of shards.  Samples are grouped in
+ * independent paths of `path_len` consecutive indices (index i: path i / path_len, step i % path_len); each path is
+ * one history in the reference's sense (step 0: raw parameters and spot0; path_len = 1: i.i.d. samples).  The
+ * exact stream definition is in csrc/dhj_generate.cuh and restated in oracle/cos_oracle.py (counter_*).
+ * (The reference's own sequential NumPy stream is kept by dhj_generator_draws for seeded drop-in runs.)
+ * Outputs, rows relative to `first`: params[n][13], spots[n], model[n][nT*nK] (maturity-major), market[n][nT*nK],
+ * loss[n].  nT*nK <= 32.
+ *   dhj_generate_dev: DEVICE pointers, asynchronous on `stream`; nothing leaves HBM.  market and loss may both be
+ *                     NULL (parameters, spots and model prices only).
+ *   dhj_generate:     HOST arrays (pinned or pageable); chunks are generated, priced and copied back double-buffered. */
+DHJ_API int dhj_generate_dev(dhj_ctx* ctx, uint64_t seed, int64_t first, int64_t n, int32_t path_len, const double* lo,
+                             const double* hi, double persistence, double spot0, double ret_mean, double ret_sd,
+                             double noise_sd, const double* strikes_rel, int32_t nK, const double* maturities,
+                             int32_t nT, double r, int32_t N, double L, double* d_params, double* d_spots,
+                             double* d_model, double* d_market, double* d_loss, void* stream);
+DHJ_API int dhj_generate(dhj_ctx* ctx, uint64_t seed, int64_t first, int64_t n, int32_t path_len, const double* lo,
+                         const double* hi, double persistence, double spot0, double ret_mean, double ret_sd,
+                         double noise_sd, const double* strikes_rel, int32_t nK, const double* maturities, int32_t nT,
+                         double r, int32_t N, double L, double* params, double* spots, double* model, double* market,
+                         double* loss);
 
 /* ---- measurement ---------------------------------------------------------------------------- */
 /* Runs a register-resident FP64 FMA-chain kernel on every SM and reports the sustained DFMA rate

@@ -14,6 +14,7 @@
 
 #include "dhj.h"
 #include "dhj_kernels.cuh"
+#include "dhj_generate.cuh"
 
 using namespace dhj;
 
@@ -112,6 +113,19 @@ struct BookHost {
   }
 };
 
+// Option books (packed slice tables + shared strike row) live in a small ring of device slots, so that a call
+// with a new (K, T) table neither waits for the device nor disturbs launches that still read an older table
+// (DoubleHeston(...).pricing() changes the book on every call; the previous design synchronised the whole device).
+constexpr int kBookSlots = 8;
+struct BookSlot {
+  DevBuf d;
+  PinBuf h;
+  std::vector<unsigned char> image;     // what the slot holds (empty: nothing)
+  cudaEvent_t uploaded = nullptr;        // the H2D copy of `image`
+  cudaEvent_t last_use = nullptr;        // the last launch that reads the slot
+  cudaStream_t upload_stream = nullptr;
+};
+
 constexpr int kSlots = 2;
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -122,6 +136,13 @@ struct Slot {
   double* user_out = nullptr;
   size_t out_bytes = 0;
   bool pending = false;
+  // generator path: several destination arrays per chunk
+  struct Piece { void* dst; size_t off, bytes; };
+  std::vector<Piece> pieces;
+  void drain_pieces(void (*copy)(void*, const void*, size_t)) {
+    for (const Piece& pc : pieces) copy(pc.dst, (const unsigned char*)h_out.p + pc.off, pc.bytes);
+    pieces.clear();
+  }
 };
 
 }  // namespace
@@ -133,10 +154,10 @@ struct dhj_ctx {
   cudaStream_t stream = nullptr;
   int64_t launches = 0;
   char err[512] = "";
-  // cached option book for the pricing entry points
-  DevBuf d_book;
-  PinBuf h_book;
-  std::vector<unsigned char> book_image;      // last uploaded packed image (+ strike table) for reuse
+  // cached option books for the pricing entry points
+  BookSlot books[kBookSlots];
+  int book_next = 0;                          // ring position of the next slot to overwrite
+  int book_cur = 0;                           // slot of the last upload_book call
   Slot slots[kSlots];
   // loss path
   DevBuf d_x, d_xv, d_idx, d_f, d_fg, d_counters, d_prices;
@@ -227,7 +248,10 @@ int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_s
   return DHJ_OK;
 }
 
-// Upload (or reuse) the packed book image + shared strike table for a pricing call on `stream`.
+// Find (or upload into the ring) the packed book image + shared strike table for a pricing call on `stream`.
+// No device-wide synchronisation: a new table goes to the least recently filled slot (after the last launch that
+// read that slot has finished — normally long ago), its copy is ordered before the caller's launches by stream
+// order or an event wait, and launches that still read other slots are not disturbed.
 int upload_book(dhj_ctx* ctx, const BookHost& book, const double* shared_strikes, int n_shared,
                 cudaStream_t stream, SliceView* v) {
   const size_t bb = book.packed_bytes();
@@ -235,20 +259,38 @@ int upload_book(dhj_ctx* ctx, const BookHost& book, const double* shared_strikes
   std::vector<unsigned char> image(bb + sb);
   book.pack(image.data());
   if (n_shared) memcpy(image.data() + bb, shared_strikes, (size_t)n_shared * sizeof(double));
-  if (image != ctx->book_image) {
-    // the pinned staging area may still feed an earlier asynchronous upload
-    DHJ_CUDA(ctx, cudaDeviceSynchronize());
-    DHJ_CUDA(ctx, ctx->d_book.reserve(image.size()));
-    DHJ_CUDA(ctx, ctx->h_book.reserve(image.size()));
-    memcpy(ctx->h_book.p, image.data(), image.size());
-    DHJ_CUDA(ctx, cudaMemcpyAsync(ctx->d_book.p, ctx->h_book.p, image.size(), cudaMemcpyHostToDevice, stream));
-    // later calls may use other streams: make the table visible to all of them
-    DHJ_CUDA(ctx, cudaStreamSynchronize(stream));
-    ctx->book_image.swap(image);
+  int hit = -1;
+  for (int i = 0; i < kBookSlots && hit < 0; ++i)
+    if (ctx->books[i].image == image) hit = i;
+  if (hit < 0) {
+    hit = ctx->book_next;
+    ctx->book_next = (ctx->book_next + 1) % kBookSlots;
+    BookSlot& b = ctx->books[hit];
+    b.image.clear();
+    // the slot's device table may still be read, its pinned staging may still feed the previous upload
+    DHJ_CUDA(ctx, cudaEventSynchronize(b.last_use));
+    DHJ_CUDA(ctx, cudaEventSynchronize(b.uploaded));
+    DHJ_CUDA(ctx, b.d.reserve(image.size()));
+    DHJ_CUDA(ctx, b.h.reserve(image.size()));
+    memcpy(b.h.p, image.data(), image.size());
+    DHJ_CUDA(ctx, cudaMemcpyAsync(b.d.p, b.h.p, image.size(), cudaMemcpyHostToDevice, stream));
+    DHJ_CUDA(ctx, cudaEventRecord(b.uploaded, stream));
+    b.upload_stream = stream;
+    b.image.swap(image);
+  } else if (ctx->books[hit].upload_stream != stream) {
+    DHJ_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->books[hit].uploaded, 0));
   }
-  book.view(v, (const unsigned char*)ctx->d_book.p);
-  v->strike = n_shared ? (const double*)((const unsigned char*)ctx->d_book.p + bb) : nullptr;
+  ctx->book_cur = hit;
+  const BookSlot& b = ctx->books[hit];
+  book.view(v, (const unsigned char*)b.d.p);
+  v->strike = n_shared ? (const double*)((const unsigned char*)b.d.p + bb) : nullptr;
   v->strike_stride = 0;
+  return DHJ_OK;
+}
+
+// the launches of the current call on `stream` read the current book slot
+int book_used(dhj_ctx* ctx, cudaStream_t stream) {
+  DHJ_CUDA(ctx, cudaEventRecord(ctx->books[ctx->book_cur].last_use, stream));
   return DHJ_OK;
 }
 
@@ -293,11 +335,25 @@ int run_price_host(dhj_ctx* ctx, SliceView v, int max_slice, const double* param
     for (; left > 0; left -= chunk) sizes.push_back(std::min(chunk, left));
     sizes.insert(sizes.end(), tail.rbegin(), tail.rend());
   }
+  // A previous call on this context may have failed half-way (DHJ_ERR_NOMEM is recoverable) and left a staged
+  // chunk behind: its caller's buffer is gone, so nothing of it may be copied out now.  Drain and forget.
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& sl = ctx->slots[i];
+    DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));
+    sl.pending = false; sl.user_out = nullptr; sl.out_bytes = 0; sl.pieces.clear();
+    // the option book was uploaded on another stream
+    DHJ_CUDA(ctx, cudaStreamWaitEvent(sl.stream, ctx->books[ctx->book_cur].uploaded, 0));
+  }
+  // DHJ_DEBUG_FAIL_AT_CHUNK (test hook, tests/test_gpu_dropin.py): return DHJ_ERR_NOMEM before that chunk is staged,
+  // as a failed allocation would, with earlier chunks still in flight
+  const char* fail_env = getenv("DHJ_DEBUG_FAIL_AT_CHUNK");
+  const long fail_at = fail_env ? atol(fail_env) : -1;
   int slot_i = 0;
   int64_t lo = 0;
   for (size_t ci = 0; ci < sizes.size(); lo += sizes[ci], ++ci, slot_i ^= 1) {
     const int64_t n = sizes[ci];
     Slot& sl = ctx->slots[slot_i];
+    if ((long)ci == fail_at) return fail(ctx, DHJ_ERR_NOMEM, "injected failure at chunk %ld (DHJ_DEBUG_FAIL_AT_CHUNK)", fail_at);
     // the slot's previous chunk must have left its buffers
     DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));
     if (sl.pending) { host_copy(sl.user_out, sl.h_out.p, sl.out_bytes); sl.pending = false; }
@@ -410,6 +466,10 @@ int dhj_init(int device, dhj_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   cudaError_t e2 = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < kBookSlots && e2 == cudaSuccess; ++i) {
+    e2 = cudaEventCreateWithFlags(&ctx->books[i].uploaded, cudaEventDisableTiming);
+    if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->books[i].last_use, cudaEventDisableTiming);
+  }
   for (int i = 0; i < kSlots && e2 == cudaSuccess; ++i) {
     e2 = cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking);
     if (e2 == cudaSuccess) e2 = cudaEventCreateWithFlags(&ctx->slots[i].done, cudaEventDisableTiming);
@@ -438,7 +498,12 @@ int dhj_destroy(dhj_ctx* ctx) {
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  ctx->d_book.release(); ctx->h_book.release();
+  for (int i = 0; i < kBookSlots; ++i) {
+    BookSlot& b = ctx->books[i];
+    b.d.release(); b.h.release();
+    if (b.uploaded) cudaEventDestroy(b.uploaded);
+    if (b.last_use) cudaEventDestroy(b.last_use);
+  }
   ctx->d_x.release(); ctx->d_xv.release(); ctx->d_idx.release(); ctx->d_f.release(); ctx->d_fg.release();
   ctx->d_counters.release(); ctx->d_prices.release(); ctx->h_x.release(); ctx->h_res.release();
   ctx->d_peak.release();
@@ -521,7 +586,9 @@ int dhj_price_grid_dev(dhj_ctx* ctx, const double* d_params, int64_t P, const do
   PriceArgs a;
   a.params = d_params; a.S0 = d_S0; a.s0_stride = s0_stride; a.row_index = nullptr; a.P = P; a.transform = 0;
   a.out = d_out;
-  return launch_price(ctx, v, a, nK, st);
+  rc = launch_price(ctx, v, a, nK, st);
+  if (rc) return rc;
+  return book_used(ctx, st);
 }
 
 // ---- calibration loss ------------------------------------------------------------------------
@@ -804,6 +871,160 @@ int dhj_chi_psi(dhj_ctx* ctx, const int32_t* k, int32_t n, double c, double d, d
   memcpy(out_psi, (unsigned char*)ctx->h_res.p + ob, ob);
   return DHJ_OK;
 }
+
+}  // extern "C"
+
+// ---- synthetic dataset sweep (counter stream; dhj_generate.cuh) ------------------------------------
+namespace {
+
+struct GenConfig {
+  GenArgs g;
+  int nK, nT, N;
+  double r, L;
+  const double* strikes_rel;
+  const double* maturities;
+};
+
+int check_generate(dhj_ctx* ctx, int64_t first, int64_t n, int32_t path_len, const double* lo, const double* hi,
+                   const double* strikes_rel, int32_t nK, const double* maturities, int32_t nT, int32_t N) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  if (first < 0 || n < 0) return fail(ctx, DHJ_ERR_ARG, "first and n must be >= 0");
+  if (path_len < 1) return fail(ctx, DHJ_ERR_ARG, "path_len must be >= 1 (got %d)", path_len);
+  if (!lo || !hi || !strikes_rel || !maturities) return fail(ctx, DHJ_ERR_ARG, "null table");
+  if (nK < 1 || nT < 1 || (int64_t)nK * nT > kGenMaxOptions)
+    return fail(ctx, DHJ_ERR_ARG, "the generator grid must have 1..%d options (got %d x %d)", kGenMaxOptions, nT, nK);
+  if (N < 1) return fail(ctx, DHJ_ERR_ARG, "N must be >= 1 (got %d)", N);
+  return DHJ_OK;
+}
+
+// enqueue draws -> prices -> market/loss for samples [first, first + n) on `st`; all pointers are device memory
+int enqueue_generate(dhj_ctx* ctx, const GenConfig& c, int64_t first, int64_t n, double* d_params, double* d_spots,
+                     double* d_model, double* d_market, double* d_loss, cudaStream_t st) {
+  if (n == 0) return DHJ_OK;
+  GenArgs g = c.g;
+  g.first = first; g.n = n;
+  const long long q_first = first / g.path_len, q_last = (first + n - 1) / g.path_len;
+  const long long paths = q_last - q_first + 1;
+  k_gen_draws<<<(unsigned)((paths + kGenWarps - 1) / kGenWarps), 32 * kGenWarps, 0, st>>>(g, d_params, d_spots);
+  DHJ_CUDA(ctx, cudaGetLastError());
+  ctx->launches++;
+  SliceView v;
+  int rc = grid_view(ctx, c.strikes_rel, c.nK, c.maturities, c.nT, /*scale_by_spot=*/1, /*is_call=*/1, c.N, c.r, 0.0,
+                     c.L, st, &v);
+  if (rc) return rc;
+  PriceArgs a;
+  a.params = d_params; a.S0 = d_spots; a.s0_stride = 1; a.row_index = nullptr; a.P = n; a.transform = 0;
+  a.out = d_model;
+  rc = launch_price(ctx, v, a, c.nK, st);
+  if (rc) return rc;
+  rc = book_used(ctx, st);
+  if (rc) return rc;
+  if (d_market && d_loss) {
+    const int M = c.nK * c.nT;
+    const size_t smem = (size_t)kGenMarketSamples * (M | 1) * sizeof(double);
+    k_gen_market<<<(unsigned)((n + kGenMarketSamples - 1) / kGenMarketSamples), kGenMarketSamples, smem, st>>>(
+        g.seed, first, n, M, g.noise_sd, d_model, d_market, d_loss);
+    DHJ_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+  }
+  return DHJ_OK;
+}
+
+void fill_gen_config(GenConfig* c, uint64_t seed, int32_t path_len, const double* lo, const double* hi,
+                     double persistence, double spot0, double ret_mean, double ret_sd, double noise_sd,
+                     const double* strikes_rel, int32_t nK, const double* maturities, int32_t nT, double r, int32_t N,
+                     double L) {
+  c->g.seed = seed; c->g.first = 0; c->g.n = 0; c->g.path_len = path_len;
+  for (int j = 0; j < kNumParams; ++j) { c->g.lo[j] = lo[j]; c->g.range[j] = hi[j] - lo[j]; }
+  c->g.persistence = persistence; c->g.spot0 = spot0; c->g.ret_mean = ret_mean; c->g.ret_sd = ret_sd;
+  c->g.noise_sd = noise_sd;
+  c->nK = nK; c->nT = nT; c->N = N; c->r = r; c->L = L; c->strikes_rel = strikes_rel; c->maturities = maturities;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dhj_generate_dev(dhj_ctx* ctx, uint64_t seed, int64_t first, int64_t n, int32_t path_len, const double* lo,
+                     const double* hi, double persistence, double spot0, double ret_mean, double ret_sd,
+                     double noise_sd, const double* strikes_rel, int32_t nK, const double* maturities, int32_t nT,
+                     double r, int32_t N, double L, double* d_params, double* d_spots, double* d_model,
+                     double* d_market, double* d_loss, void* stream) {
+  int rc = check_generate(ctx, first, n, path_len, lo, hi, strikes_rel, nK, maturities, nT, N);
+  if (rc) return rc;
+  if (!d_params || !d_spots || !d_model) return fail(ctx, DHJ_ERR_ARG, "null output (params, spots, model are required)");
+  if ((d_market == nullptr) != (d_loss == nullptr))
+    return fail(ctx, DHJ_ERR_ARG, "market and loss outputs come together (both or neither)");
+  DHJ_CUDA(ctx, cudaSetDevice(ctx->device));
+  GenConfig c;
+  fill_gen_config(&c, seed, path_len, lo, hi, persistence, spot0, ret_mean, ret_sd, noise_sd, strikes_rel, nK,
+                  maturities, nT, r, N, L);
+  return enqueue_generate(ctx, c, first, n, d_params, d_spots, d_model, d_market, d_loss, (cudaStream_t)stream);
+}
+
+int dhj_generate(dhj_ctx* ctx, uint64_t seed, int64_t first, int64_t n, int32_t path_len, const double* lo,
+                 const double* hi, double persistence, double spot0, double ret_mean, double ret_sd, double noise_sd,
+                 const double* strikes_rel, int32_t nK, const double* maturities, int32_t nT, double r, int32_t N,
+                 double L, double* params, double* spots, double* model, double* market, double* loss) {
+  int rc = check_generate(ctx, first, n, path_len, lo, hi, strikes_rel, nK, maturities, nT, N);
+  if (rc) return rc;
+  if (!params || !spots || !model || !market || !loss) return fail(ctx, DHJ_ERR_ARG, "null output array");
+  if (n == 0) return DHJ_OK;
+  DHJ_CUDA(ctx, cudaSetDevice(ctx->device));
+  GenConfig c;
+  fill_gen_config(&c, seed, path_len, lo, hi, persistence, spot0, ret_mean, ret_sd, noise_sd, strikes_rel, nK,
+                  maturities, nT, r, N, L);
+  const int M = nK * nT;
+  const bool pinned = is_pinned_host(params) && is_pinned_host(spots) && is_pinned_host(model) &&
+                      is_pinned_host(market) && is_pinned_host(loss);
+  // chunks of whole paths where possible (a chunk that starts inside a path re-draws the path's head)
+  int64_t chunk = 131072;
+  if (path_len < chunk) chunk -= chunk % path_len;
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& sl = ctx->slots[i];
+    DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));
+    sl.pending = false; sl.user_out = nullptr; sl.out_bytes = 0; sl.pieces.clear();
+  }
+  int slot_i = 0;
+  for (int64_t lo_i = 0; lo_i < n; lo_i += chunk, slot_i ^= 1) {
+    const int64_t cnt = std::min(chunk, n - lo_i);
+    Slot& sl = ctx->slots[slot_i];
+    DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));
+    sl.drain_pieces(host_copy);
+    // device layout of a chunk: params | spots | model | market | loss
+    const size_t pb = (size_t)cnt * kNumParams * sizeof(double), sb = (size_t)cnt * sizeof(double);
+    const size_t mb = (size_t)cnt * M * sizeof(double);
+    const size_t total = pb + sb + 2 * mb + sb;
+    DHJ_CUDA(ctx, sl.d_out.reserve(total));
+    unsigned char* d = (unsigned char*)sl.d_out.p;
+    double* d_params = (double*)d; double* d_spots = (double*)(d + pb); double* d_model = (double*)(d + pb + sb);
+    double* d_market = (double*)(d + pb + sb + mb); double* d_loss = (double*)(d + pb + sb + 2 * mb);
+    rc = enqueue_generate(ctx, c, first + lo_i, cnt, d_params, d_spots, d_model, d_market, d_loss, sl.stream);
+    if (rc) return rc;
+    void* dst[5] = {params + lo_i * kNumParams, spots + lo_i, model + lo_i * M, market + lo_i * M, loss + lo_i};
+    const size_t off[5] = {0, pb, pb + sb, pb + sb + mb, pb + sb + 2 * mb};
+    const size_t len[5] = {pb, sb, mb, mb, sb};
+    if (pinned) {
+      for (int k = 0; k < 5; ++k)
+        DHJ_CUDA(ctx, cudaMemcpyAsync(dst[k], d + off[k], len[k], cudaMemcpyDeviceToHost, sl.stream));
+    } else {
+      DHJ_CUDA(ctx, sl.h_out.reserve(total));
+      DHJ_CUDA(ctx, cudaMemcpyAsync(sl.h_out.p, d, total, cudaMemcpyDeviceToHost, sl.stream));
+      for (int k = 0; k < 5; ++k) sl.pieces.push_back({dst[k], off[k], len[k]});
+    }
+    DHJ_CUDA(ctx, cudaEventRecord(sl.done, sl.stream));
+  }
+  for (int i = 0; i < kSlots; ++i) {
+    Slot& sl = ctx->slots[i];
+    DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));
+    sl.drain_pieces(host_copy);
+  }
+  return DHJ_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- measurement -----------------------------------------------------------------------------
 int dhj_fp64_peak(dhj_ctx* ctx, int32_t iters, double* tflops, double* milliseconds) {

@@ -25,7 +25,7 @@ EXPORTS = (
     "dhj_market_create", "dhj_market_destroy", "dhj_loss_batch", "dhj_loss_fd", "dhj_market_prices",
     "dhj_cf", "dhj_truncation_range", "dhj_chi_psi", "dhj_fp64_peak",
     "dhj_lbfgs_create", "dhj_lbfgs_destroy", "dhj_lbfgs_ask", "dhj_lbfgs_tell", "dhj_lbfgs_result",
-    "dhj_generator_draws",
+    "dhj_generator_draws", "dhj_generate_dev", "dhj_generate",
 )
 
 
@@ -94,6 +94,11 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.dhj_generator_draws.argtypes = [_U32, _c_i32, _c_i32, _c_f64, _c_i64, _c_i32, _F64, _F64, _c_f64, _c_f64,
                                             _c_f64, _c_f64, _c_f64, _c_i32, _F64, _F64, _F64, _U32,
                                             ctypes.POINTER(_c_i32), ctypes.POINTER(_c_i32), ctypes.POINTER(_c_f64)]
+        _c_u64 = ctypes.c_uint64
+        gen_head = [_c_vp, _c_u64, _c_i64, _c_i64, _c_i32, _F64, _F64, _c_f64, _c_f64, _c_f64, _c_f64, _c_f64, _F64,
+                    _c_i32, _F64, _c_i32, _c_f64, _c_i32, _c_f64]
+        lib.dhj_generate_dev.argtypes = gen_head + [_c_vp] * 6
+        lib.dhj_generate.argtypes = gen_head + [_c_vp] * 5
         for name in EXPORTS:
             if name not in ("dhj_last_error",):
                 getattr(lib, name).restype = ctypes.c_int
@@ -211,6 +216,47 @@ class Context:
                                                      float(q), strikes, strikes.size, maturities, maturities.size,
                                                      int(bool(scale_by_spot)), int(bool(is_call)), int(N), float(L),
                                                      d_out, stream or None), "dhj_price_grid_dev")
+
+    # -- synthetic dataset sweep (counter stream) ------------------------------------------------
+    @staticmethod
+    def _gen_args(seed, first, n, path_len, lo, hi, persistence, spot0, ret_mean, ret_sd, noise_sd, strikes_rel,
+                  maturities, r, N, L):
+        lo, hi = _f64(lo).reshape(N_PARAMS), _f64(hi).reshape(N_PARAMS)
+        strikes_rel, maturities = _f64(strikes_rel).reshape(-1), _f64(maturities).reshape(-1)
+        return (int(seed) & 0xFFFFFFFFFFFFFFFF, int(first), int(n), int(path_len), lo, hi, float(persistence),
+                float(spot0), float(ret_mean), float(ret_sd), float(noise_sd), strikes_rel, strikes_rel.size,
+                maturities, maturities.size, float(r), int(N), float(L))
+
+    def generate_dev(self, seed, first, n, path_len, lo, hi, persistence, spot0, ret_mean, ret_sd, noise_sd,
+                     strikes_rel, maturities, r, d_params: int, d_spots: int, d_model: int, d_market: int = 0,
+                     d_loss: int = 0, stream: int = 0, N=128, L=10.0):
+        """Samples [first, first+n) of the counter stream, drawn, priced and noised on the device into DEVICE
+        buffers (ints: pointers / stream handle); asynchronous (dhj_generate_dev)."""
+        args = self._gen_args(seed, first, n, path_len, lo, hi, persistence, spot0, ret_mean, ret_sd, noise_sd,
+                              strikes_rel, maturities, r, N, L)
+        with self._lock:
+            self._check(self._lib.dhj_generate_dev(self._h, *args, d_params, d_spots, d_model, d_market or None,
+                                                   d_loss or None, stream or None), "dhj_generate_dev")
+
+    def generate(self, seed, first, n, path_len, lo, hi, persistence, spot0, ret_mean, ret_sd, noise_sd, strikes_rel,
+                 maturities, r, N=128, L=10.0, out=None):
+        """Same into HOST arrays (dhj_generate): dict of params[n,13], spots[n], model[n,M], market[n,M], loss[n].
+        `out` may hold preallocated (e.g. pinned) arrays under those keys."""
+        args = self._gen_args(seed, first, n, path_len, lo, hi, persistence, spot0, ret_mean, ret_sd, noise_sd,
+                              strikes_rel, maturities, r, N, L)
+        n, M = int(n), args[12] * args[14]
+        shapes = {"params": (n, N_PARAMS), "spots": (n,), "model": (n, M), "market": (n, M), "loss": (n,)}
+        res = {}
+        for key, shp in shapes.items():
+            a = None if out is None else out.get(key)
+            if a is None:
+                a = np.empty(shp, dtype=np.float64)
+            elif a.dtype != np.float64 or a.size != int(np.prod(shp)) or not a.flags.c_contiguous:
+                raise ValueError(f"out[{key!r}] must be C-contiguous float64{list(shp)}")
+            res[key] = a
+        with self._lock:
+            self._check(self._lib.dhj_generate(self._h, *args, *[_ptr(res[k]) for k in shapes]), "dhj_generate")
+        return {k: res[k].reshape(shapes[k]) for k in shapes}
 
     # -- the remaining DoubleHeston methods -------------------------------------------------------
     def cf(self, params, r, q, tau, u) -> np.ndarray:
@@ -339,6 +385,10 @@ class BatchLBFGS:
             f, g = evaluate(x, idx)               # e.g. Market.loss_fd(x, market_index=...)
             opt.tell(f, g)
         x, f, nit, nfev, status = opt.result()
+
+    `maxfun` counts (f, g) requests.  The reference lets scipy difference the loss itself (jac=None), where each
+    request costs 14 loss evaluations against scipy's default maxfun = 15000: the equivalent request limit is
+    15000 // 14 = 1071, the default here (and what the drop-in `calibrate` passes to scipy).
     """
 
     MESSAGES = ("CONVERGENCE: NORM OF PROJECTED GRADIENT <= PGTOL",
@@ -347,7 +397,7 @@ class BatchLBFGS:
                 "STOP: TOTAL NO. OF F,G EVALUATIONS EXCEEDS LIMIT",
                 "ABNORMAL: ")
 
-    def __init__(self, x0, maxiter=300, ftol=1e-9, gtol=1e-6, m=10, maxfun=15000, maxls=20):
+    def __init__(self, x0, maxiter=300, ftol=1e-9, gtol=1e-6, m=10, maxfun=15000 // 14, maxls=20):
         self._lib = load_library()
         x0 = _f64(x0)
         if x0.ndim != 2:

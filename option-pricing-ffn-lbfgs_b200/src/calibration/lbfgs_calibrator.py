@@ -40,6 +40,10 @@ from dhj import default_context  # noqa: E402
 
 _SENTINEL = 1e10       # :152-153
 _FD_STEP = 1e-8        # scipy's L-BFGS-B `eps` default, what jac=None uses
+# scipy's default maxfun = 15000 counts LOSS evaluations; with jac=None every (f, g) request costs 14 of them
+# (1 + 13 forward points), so the reference stops after 1072 requests (14 * 1072 > 15000).  The drop-in answers a
+# request with one call (jac=True), which scipy counts as 1: the same limit is 15000 // 14 = 1071 requests.
+_MAXFUN_REQUESTS = 15000 // 14
 
 
 @dataclass
@@ -231,7 +235,7 @@ class DoubleHestonJumpCalibrator:
     @staticmethod
     def _minimize(fun_and_grad, x0, maxiter):
         return minimize(fun=fun_and_grad, x0=x0, jac=True, method='L-BFGS-B',
-                        options={'maxiter': maxiter, 'ftol': 1e-9, 'gtol': 1e-6})
+                        options={'maxiter': maxiter, 'ftol': 1e-9, 'gtol': 1e-6, 'maxfun': _MAXFUN_REQUESTS})
 
     def calibrate(self, maxiter: int = 300, multi_start: int = 3, *, x0=None) -> CalibrationResult:
         """Calibrate to the market prices with `multi_start` L-BFGS-B runs; the best (lowest loss) wins.

@@ -19,7 +19,17 @@ instead of 19 s of Python loop.
 For datasets too large for a list of Python objects: `generate_synthetic_arrays` returns flat
 arrays (optionally written as .npz or as a directory of .npy files that can be memory-mapped), and
 `SyntheticCalibrationSet` presents such arrays as a lazy sequence of `CalibrationResult` objects.
+
+For sweeps that must not depend on one sequential host stream (BASELINE config 4: 100 M samples sharded over
+1/2/4/8 GPUs) `generate_synthetic_arrays(n, seed=...)` switches to the library's COUNTER STREAM
+(`dhj_generate`, csrc/dhj_generate.cuh): parameters, spots and noise are drawn ON THE DEVICE as Philox functions of
+(seed, sample index), priced, noised and reduced to the per-sample loss there; samples are grouped in independent
+reference-style histories of `path_len` steps.  With `sharded=True` every rank of the process group produces and
+writes its own block of histories (`shard-RRRRR-of-WWWWW/` under `save_path`), and the union of the shards is the
+same dataset whatever the number of ranks.
 """
+import json
+import operator
 import pickle
 import sys
 from datetime import datetime, timedelta
@@ -86,6 +96,9 @@ def _save_arrays(data, save_path):
     for k in _ARRAY_KEYS:
         np.save(Path(save_path) / f'{k}.npy', data[k])
     np.save(Path(save_path) / 'param_names.npy', np.asarray(data['param_names']))
+    for k in ('_first', '_path_len'):
+        if k in data:
+            np.save(Path(save_path) / f'{k}.npy', np.asarray(int(data[k])))
 
 
 class SyntheticCalibrationSet:
@@ -102,9 +115,12 @@ class SyntheticCalibrationSet:
         path = str(path)
         if path.endswith('.npz'):
             z = np.load(path)
-            return cls({k: z[k] for k in z.files})
+            return cls({k: (int(z[k]) if k.startswith('_') else z[k]) for k in z.files})
         d = {k: np.load(Path(path) / f'{k}.npy', mmap_mode='r' if mmap else None) for k in _ARRAY_KEYS}
         d['param_names'] = np.load(Path(path) / 'param_names.npy')
+        for k in ('_first', '_path_len'):
+            if (Path(path) / f'{k}.npy').exists():
+                d[k] = int(np.load(Path(path) / f'{k}.npy'))
         return cls(d)
 
     def save(self, path):
@@ -113,15 +129,25 @@ class SyntheticCalibrationSet:
     def __len__(self):
         return int(self.data['spots'].shape[0])
 
+    def _history_step(self, i):
+        """Trading-day number of local sample i: its global index, modulo the history length for counter-stream
+        datasets (every history starts on 2022-01-03 like the reference's single one)."""
+        g = int(self.data.get('_first', 0)) + i
+        path_len = int(self.data.get('_path_len', 0))
+        return g % path_len if path_len > 0 else g
+
     def __getitem__(self, i):
         d = self.data
         if isinstance(i, slice):
             sub = {k: (d[k][i] if k != 'maturities' else d[k]) for k in _ARRAY_KEYS}
             sub['param_names'] = d['param_names']
-            sub['_first'] = d.get('_first', 0) + (i.indices(len(self))[0] if len(self) else 0)
+            sub['_first'] = int(d.get('_first', 0)) + (i.indices(len(self))[0] if len(self) else 0)
+            if '_path_len' in d:
+                sub['_path_len'] = int(d['_path_len'])
             assert i.step in (None, 1), "contiguous slices only"
             return SyntheticCalibrationSet(sub)
         n = len(self)
+        i = operator.index(i)                 # NumPy integer indices (np.random.permutation, np.arange) included
         if i < 0:
             i += n
         if not 0 <= i < n:
@@ -130,7 +156,7 @@ class SyntheticCalibrationSet:
         options = [{'strike': d['strikes'][i, j], 'maturity': mats[j], 'price': d['market_prices'][i, j],
                     'option_type': 'call'} for j in range(mats.size)]
         return CalibrationResult(
-            date=_trading_date(d.get('_first', 0) + i), spot=d['spots'][i], risk_free=RISK_FREE,
+            date=_trading_date(self._history_step(i)), spot=d['spots'][i], risk_free=RISK_FREE,
             parameters={name: d['params'][i, k] for k, name in enumerate(self.param_names)},
             market_prices=np.array(d['market_prices'][i]), model_prices=np.array(d['model_prices'][i]),
             market_options=options, final_loss=d['losses'][i],
@@ -150,13 +176,67 @@ def _trading_date(i):
         return f'2022-01-03+{i}bd'
 
 
-def generate_synthetic_arrays(n_samples, ctx=None, save_path=None):
+def generate_synthetic_arrays(n_samples, ctx=None, save_path=None, *, seed=None, path_len=500, first=0,
+                              sharded=False, group=None):
     """Flat-array form of the generator: dict of params[n,13], spots[n], strikes[n,15], maturities[15],
     model_prices[n,15], market_prices[n,15], losses[n] (same values as the object form).  With `save_path` the
     arrays are also written — `*.npz`: one archive; any other path: a directory of .npy files that
     `SyntheticCalibrationSet.load` memory-maps — the on-disk form for datasets too large for a pickle of Python
-    objects."""
+    objects.
+
+    `seed=None` (default): the reference's stream — the global NumPy RNG, one history of n samples, bit-compatible
+    with `generate_synthetic_calibrations` (prices on the device, draws / noise / loss on the host).
+    `seed=<int>`: the library's counter stream (`dhj_generate`): samples [first, first + n) of the dataset `seed`,
+    drawn, priced, noised and reduced to losses on the device; independent histories of `path_len` samples.
+    `sharded=True` (counter stream only): this rank's block of whole histories of the n-sample dataset
+    (`dhj.shard.shard_bounds` over histories), written to `save_path/shard-RRRRR-of-WWWWW/` when `save_path` is
+    given; the returned dict carries `_first` (global index of its first sample).  Without a process group the
+    single shard is the whole dataset."""
     ctx = ctx or default_context()
+    if seed is None:
+        if sharded or first:
+            raise ValueError("the reference's NumPy stream is sequential: `first` / `sharded` need `seed=`")
+        return _generate_numpy_stream(n_samples, ctx, save_path)
+    n_samples, path_len, first = int(n_samples), int(path_len), int(first)
+    rank = world = None
+    if sharded:
+        from dhj.shard import _dist, shard_bounds
+        dist = _dist()
+        world = dist.get_world_size(group) if dist else 1
+        rank = dist.get_rank(group) if dist else 0
+        n_paths = -(-n_samples // path_len)
+        q_lo, q_hi = shard_bounds(n_paths, world, rank)
+        lo_i, hi_i = min(n_samples, q_lo * path_len), min(n_samples, q_hi * path_len)
+        first, n_samples = first + lo_i, hi_i - lo_i
+    lo = np.array([v[0] for v in PARAM_RANGES.values()])
+    hi = np.array([v[1] for v in PARAM_RANGES.values()])
+    g = ctx.generate(seed, first, n_samples, path_len, lo, hi, PERSISTENCE, SPOT_BASE, 0.0003, 0.01, 0.02,
+                     STRIKES.astype(np.float64), MATURITIES, RISK_FREE)
+    spots = g['spots']
+    data = {'param_names': list(PARAM_RANGES), 'params': g['params'], 'spots': spots,
+            'strikes': np.tile(STRIKES[None, :] * spots[:, None] / 100.0, (1, MATURITIES.size)),
+            'maturities': np.repeat(MATURITIES, STRIKES.size), 'model_prices': g['model'],
+            'market_prices': g['market'], 'losses': g['loss'], '_first': first, '_path_len': path_len}
+    if save_path is not None:
+        if sharded:
+            shard_dir = Path(save_path) / f'shard-{rank:05d}-of-{world:05d}'
+            _save_arrays(data, shard_dir)
+            with open(shard_dir / 'manifest.json', 'w') as f:
+                json.dump({'seed': int(seed), 'first': first, 'n': n_samples, 'path_len': path_len, 'rank': rank,
+                           'world': world, 'stream': 'counter (Philox4x32-10, csrc/dhj_generate.cuh)'}, f)
+        else:
+            _save_arrays(data, save_path)
+    return data
+
+
+def load_sharded(save_path):
+    """The shards a `generate_synthetic_arrays(..., sharded=True, save_path=...)` run wrote, in dataset order:
+    list of memory-mapped `SyntheticCalibrationSet`s (each knows the global index of its first sample)."""
+    dirs = sorted(Path(save_path).glob('shard-*-of-*'))
+    return [SyntheticCalibrationSet.load(d, mmap=True) for d in dirs]
+
+
+def _generate_numpy_stream(n_samples, ctx, save_path):
     names, params, spots, noise = _draw_inputs(n_samples)
     model = ctx.price_grid(params, spots, STRIKES.astype(np.float64), MATURITIES, RISK_FREE,
                            scale_by_spot=True, is_call=True).reshape(n_samples, MATURITIES.size * STRIKES.size)

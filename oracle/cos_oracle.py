@@ -371,6 +371,107 @@ def generator_draws(n, rng=np.random):
 
 
 # ----------------------------------------------------------------------------------------------
+# counter stream of the device-resident dataset sweep (the product's definition: csrc/dhj_generate.cuh header;
+# per-sample semantics of src/data/synthetic_generator.py:98-157 with draws that depend on the sample index only)
+# ----------------------------------------------------------------------------------------------
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+COUNTER_STREAM_TAG = 0x44484A31
+_MASK32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(counter, key):
+    """Philox4x32-10 (Salmon et al., SC'11; Random123).  counter[..., 4], key[..., 2] of uint32 -> uint32[..., 4]."""
+    c = [np.asarray(counter[..., j], dtype=np.uint64) for j in range(4)]
+    k0 = np.asarray(key[..., 0], dtype=np.uint64)
+    k1 = np.asarray(key[..., 1], dtype=np.uint64)
+    for _ in range(10):
+        p0 = _PHILOX_M0 * c[0]
+        p1 = _PHILOX_M1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & _MASK32, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & _MASK32]
+        k0 = (k0 + np.uint64(_PHILOX_W0)) & _MASK32
+        k1 = (k1 + np.uint64(_PHILOX_W1)) & _MASK32
+    return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def counter_words(seed, index, slot):
+    """The two 64-bit words of (sample index, slot): w0 = x0 | x1 << 32, w1 = x2 | x3 << 32."""
+    index = np.asarray(index, dtype=np.uint64)
+    ctr = np.stack([index & _MASK32, index >> np.uint64(32), np.full(index.shape, slot, dtype=np.uint64),
+                    np.full(index.shape, COUNTER_STREAM_TAG, dtype=np.uint64)], axis=-1)
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    key = np.broadcast_to(np.array([seed & 0xFFFFFFFF, seed >> 32], dtype=np.uint64), index.shape + (2,))
+    x = philox4x32_10(ctr, key).astype(np.uint64)
+    return x[..., 0] | (x[..., 1] << np.uint64(32)), x[..., 2] | (x[..., 3] << np.uint64(32))
+
+
+def counter_uniform(w):
+    return (w >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
+
+def counter_normal_pair(seed, index, slot):
+    """Box-Muller pair: u1 = ((w0 >> 11) + 1) 2^-53 in (0, 1], u2 = (w1 >> 11) 2^-53."""
+    w0, w1 = counter_words(seed, index, slot)
+    u1 = ((w0 >> np.uint64(11)) + np.uint64(1)).astype(np.float64) * 2.0 ** -53
+    R = np.sqrt(-2.0 * np.log(u1))
+    ang = 2.0 * np.pi * counter_uniform(w1)
+    return R * np.cos(ang), R * np.sin(ang)
+
+
+def counter_draws(seed, first, n, path_len, lo=None, hi=None, persistence=0.9, spot0=100.0, ret_mean=0.0003,
+                  ret_sd=0.01, noise_sd=0.02, n_noise=15):
+    """params[n,13], spots[n], noise[n,n_noise] for samples [first, first+n) of the counter stream.
+
+    Sample i is step t = i % path_len of path i // path_len; per path the reference's recurrences
+    (synthetic_generator.py:100-116): raw uniforms, AR(1) smoothing from step 1 on, spot walk from spot0.
+    """
+    lo = GENERATOR_RANGES[:, 0] if lo is None else np.asarray(lo, dtype=np.float64)
+    hi = GENERATOR_RANGES[:, 1] if hi is None else np.asarray(hi, dtype=np.float64)
+    first, n, path_len = int(first), int(n), int(path_len)
+    start = (first // path_len) * path_len                    # head of the first path touched
+    idx = np.arange(start, first + n, dtype=np.uint64)
+    raw = np.empty((idx.size, N_PARAMS))
+    for s in range(7):
+        w0, w1 = counter_words(seed, idx, s)
+        raw[:, 2 * s] = lo[2 * s] + (hi[2 * s] - lo[2 * s]) * counter_uniform(w0)
+        if 2 * s + 1 < N_PARAMS:
+            raw[:, 2 * s + 1] = lo[2 * s + 1] + (hi[2 * s + 1] - lo[2 * s + 1]) * counter_uniform(w1)
+    z0, _ = counter_normal_pair(seed, idx, 7)
+    ret = ret_mean + ret_sd * z0
+    params = np.empty_like(raw)
+    spots = np.empty(idx.size)
+    t = (idx % np.uint64(path_len)).astype(np.int64)
+    one_minus = 1.0 - persistence
+    for r in range(idx.size):                                 # sequential inside a path, as in the reference
+        if t[r] == 0:
+            params[r] = raw[r]
+            spots[r] = spot0
+        else:
+            params[r] = persistence * params[r - 1] + one_minus * raw[r]
+            spots[r] = spots[r - 1] * (1.0 + ret[r])
+    noise = np.empty((idx.size, n_noise))
+    for c in range((n_noise + 1) // 2):
+        za, zb = counter_normal_pair(seed, idx, 8 + c)
+        noise[:, 2 * c] = noise_sd * za
+        if 2 * c + 1 < n_noise:
+            noise[:, 2 * c + 1] = noise_sd * zb
+    cut = first - start
+    return params[cut:], spots[cut:], noise[cut:]
+
+
+def counter_generate(seed, first, n, path_len, r=GENERATOR_RATE, N=128, **kw):
+    """Full restatement of the sweep: draws, C-oracle prices on the generator grid (K = K_rel * spot / 100,
+    :123-138), market = price + noise * price (:141-142), loss = mean(((model - market) / market)^2) (:154-157)."""
+    params, spots, noise = counter_draws(seed, first, n, path_len, **kw)
+    K = np.tile(GENERATOR_STRIKES_REL[None, :] * spots[:, None] / 100.0, (1, GENERATOR_MATURITIES.size))
+    T = np.repeat(GENERATOR_MATURITIES, GENERATOR_STRIKES_REL.size)
+    model = c_price_batch(params, spots, K, T, np.ones(T.size), r, 0.0, N)
+    market = model + noise * model
+    loss = np.mean(((model - market) / market) ** 2, axis=1)
+    return {"params": params, "spots": spots, "noise": noise, "model": model, "market": market, "loss": loss}
+
+
+# ----------------------------------------------------------------------------------------------
 # C restatement (oracle/cos_oracle.c), OpenMP over options: same arithmetic as the scalar port, ~1000x faster
 # ----------------------------------------------------------------------------------------------
 _C_LIB = None

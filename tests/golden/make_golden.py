@@ -22,6 +22,8 @@ Fixtures (all float64, written with numpy.savez so values round-trip bit-exactly
   initial_guess.npz    get_initial_guess(0/1/2) under np.random.seed(0) (lbfgs_calibrator.py:179-234)
   generator_seed42.npz generate_synthetic_calibrations(20) under np.random.seed(42)
   calib_ensemble.npz   (--slow) final losses of the reference from ulp-perturbed copies of start 1's x0
+  calib_noisy.npz      (--slow) reference optimiser trajectories (every x, every loss) on 4 noisy generator-style
+                       markets, starts 0 and 2
   calib_trajectory.npz (--slow) every x the reference optimiser visits for the C1 market,
                        np.random.seed(0), starts 0..2, with losses, nit, messages
 """
@@ -354,6 +356,58 @@ def make_calib_ensemble():
          message=np.array([o[4] for o in out]))
 
 
+def _noisy_member(job):
+    """One reference optimiser run (jac=None, scipy's own forward differences) on a NOISY generator-style market,
+    logging every x it evaluates."""
+    from scipy.optimize import minimize
+    m, start, spot, r, opts = job
+    cal = DoubleHestonJumpCalibrator(spot, r, opts)
+    x0 = cal.get_initial_guess(start)                      # 0 and 2 only: no RNG involved
+    xs, fs = [], []
+
+    def f(x):
+        v = cal.compute_loss(x)
+        xs.append(np.array(x, dtype=float)); fs.append(float(v))
+        return v
+    t0 = time.time()
+    res = minimize(fun=f, x0=x0, method="L-BFGS-B",
+                   options={"maxiter": 300, "ftol": 1e-9, "gtol": 1e-6, "disp": False})
+    print(f"market {m} start {start}: nit={res.nit} nfev={res.nfev} fun={res.fun!r} msg={res.message} "
+          f"{time.time() - t0:.1f}s", flush=True)
+    return m, start, x0, np.array(xs), np.array(fs), res.x, float(res.fun), int(res.nit), str(res.message)
+
+
+def make_calib_noisy():
+    """(--slow) Reference trajectories on 4 noisy markets built by the generator's recipe (uniform parameters in
+    its ranges, K = K_rel * spot / 100, r = 0.03, market = price + N(0, 0.02) * price: synthetic_generator.py:98-142),
+    starts 0 (literature) and 2 (ATM-implied): every x the optimiser evaluates, with its loss."""
+    import multiprocessing as mp
+    rng = np.random.default_rng(20260105)
+    n_markets = 4
+    jobs, out = [], {}
+    for m in range(n_markets):
+        p = rng.uniform(GEN_RANGES[:, 0], GEN_RANGES[:, 1])
+        spot = float(rng.uniform(85.0, 120.0))
+        opts = []
+        for T in [0.25, 0.5, 1.0]:
+            for kr in [90, 95, 100, 105, 110]:
+                K = kr * spot / 100.0
+                price = ref_price(p, spot, K, T, 0.03)
+                opts.append({"strike": K, "maturity": T, "price": price + rng.normal(0, 0.02) * price,
+                             "option_type": "call"})
+        K, T, C, M = market_arrays(opts)
+        out.update({f"m{m}_spot": spot, f"m{m}_params": p, f"m{m}_strike": K, f"m{m}_maturity": T, f"m{m}_market": M})
+        for start in (0, 2):
+            jobs.append((m, start, spot, 0.03, opts))
+    with mp.get_context("fork").Pool(min(8, len(jobs))) as pool:
+        done = pool.map(_noisy_member, jobs, chunksize=1)
+    for m, start, x0, xs, fs, x, fun, nit, msg in done:
+        tag = f"m{m}_s{start}"
+        out.update({f"{tag}_x0": x0, f"{tag}_xs": xs, f"{tag}_fs": fs, f"{tag}_x": x, f"{tag}_fun": fun,
+                    f"{tag}_nit": nit, f"{tag}_message": msg})
+    save("calib_noisy.npz", r=0.03, n_markets=n_markets, **out)
+
+
 MAKERS = {
     "known_answers": make_known_answers,
     "prices_grid15": make_prices_grid15,
@@ -364,7 +418,8 @@ MAKERS = {
     "initial_guess": make_initial_guess,
     "generator": make_generator,
 }
-SLOW = {"calib_trajectory": make_calib_trajectory, "calib_ensemble": make_calib_ensemble}
+SLOW = {"calib_trajectory": make_calib_trajectory, "calib_ensemble": make_calib_ensemble,
+        "calib_noisy": make_calib_noisy}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

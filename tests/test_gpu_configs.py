@@ -1,0 +1,306 @@
+"""GPU parity at the sizes BASELINE.json names (C3 dense surface, C4 dataset sweep, C5 batched calibrations) and the
+calibrator's final-loss clause, all through the C-ABI of libdhj.so.
+
+Tolerances (north-star): 1e-10 relative price error, 1e-9 absolute loss error per evaluation; final calibrated
+losses: 1e-6 relative where the reference's own run is reproducible (starts that stall at iteration 0), and
+membership in the reference's own ulp-perturbation spread where it is chaotic.
+"""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from conftest import PKG, rel_err
+from oracle import cos_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PRICE_RTOL = 1e-10
+LOSS_ATOL = 1e-9
+FINAL_LOSS_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import dhj
+    c = dhj.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import sys
+    for sub in ("models", "calibration", "data"):
+        p = os.path.join(PKG, "src", sub)
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import double_heston
+    import lbfgs_calibrator
+    import synthetic_generator
+    return double_heston, lbfgs_calibrator, synthetic_generator
+
+
+# ---- C3: the dense surface at its BASELINE shape ------------------------------------------------------------
+def _c3_params():
+    rng = np.random.default_rng(20260102)
+    return rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(1024, 13))
+
+
+def test_c3_full_shape(ctx):
+    """1 024 parameter sets x 200 strikes x 20 maturities, N = 256, ONE price_grid call (BASELINE configs[2]); 64
+    full sets (256 000 prices) against the C restatement of the reference; determinism over the whole launch."""
+    params = _c3_params()
+    Ks, Ts = np.linspace(80.0, 120.0, 200), np.linspace(0.25, 2.0, 20)
+    got = ctx.price_grid(params, 100.0, Ks, Ts, 0.03, N=256)
+    assert got.shape == (1024, 20, 200) and np.isfinite(got).all() and (got > 0).all()
+    assert np.array_equal(got, ctx.price_grid(params, 100.0, Ks, Ts, 0.03, N=256))
+    sel = np.random.default_rng(1).choice(1024, size=64, replace=False)
+    K, T = np.tile(Ks, 20), np.repeat(Ts, 200)
+    want = O.c_price_batch(params[sel], 100.0, K, T, np.ones(K.size), 0.03, 0.0, 256).reshape(64, 20, 200)
+    err = rel_err(got[sel], want)
+    print("C3 full shape: %d prices vs C oracle, max rel err %.3e, median %.3e, min price %.3g"
+          % (want.size, err.max(), np.median(err), want.min()))
+    assert err.max() <= PRICE_RTOL
+    # monotone in strike, increasing in maturity over the whole 4 M-price launch
+    assert (np.diff(got, axis=2) < 0).all() and (np.diff(got, axis=1) > 0).all()
+
+
+def test_c3_full_shape_edge(ctx):
+    """The edge variant of SURVEY §8d: K from 50 to 150 and maturities from 0.02 — the +-0.1 widening binds, so strikes
+    get their own (a, b) and CF pass.  Deep out-of-the-money short-dated prices are rounding noise of a sum whose
+    terms are ~ max(S0, K) e^b: judged on that conditioning scale, relative elsewhere."""
+    params = _c3_params()[:256]
+    Ks = np.linspace(50.0, 150.0, 200)
+    Ts = np.concatenate([[0.02, 0.05, 0.1], np.linspace(0.25, 2.0, 17)])
+    got = ctx.price_grid(params, 100.0, Ks, Ts, 0.03, N=256)
+    sel = np.arange(0, 256, 8)
+    K, T = np.tile(Ks, 20), np.repeat(Ts, 200)
+    want, ab = O.c_price_batch(params[sel], 100.0, K, T, np.ones(K.size), 0.03, 0.0, 256, return_ab=True)
+    want = want.reshape(-1, 20, 200)
+    ab = ab.reshape(-1, 20, 200, 2)
+    assert (ab[..., 0].min(axis=2) < ab[..., 0].max(axis=2)).any()       # the widening binds somewhere
+    scale = np.maximum(100.0, K.reshape(20, 200))[None] * np.maximum(1.0, np.exp(ab[..., 1]))
+    err = np.abs(got[sel] - want)
+    ok = (err <= PRICE_RTOL * np.abs(want)) | (err <= 1e-13 * scale)
+    print("C3 edge: worst abs err / conditioning scale %.3e; prices >= 1e-3 S0: max rel err %.3e"
+          % ((err / scale).max(), rel_err(got[sel], want)[want >= 0.1].max()))
+    assert ok.all()
+    assert rel_err(got[sel], want)[want >= 0.1].max() <= PRICE_RTOL
+
+
+# ---- loss parity away from the noise-free C1 trajectory ----------------------------------------------------------
+def test_noisy_market_trajectory_replay(ctx, golden):
+    """Every x the REFERENCE optimiser evaluated on 4 noisy generator-style markets, starts 0 and 2 (7 056 loss
+    evaluations far from any optimum, Feller-active and sentinel points included): GPU loss within 1e-9 absolute."""
+    g = golden("calib_noisy.npz")
+    worst, n_eval = 0.0, 0
+    for m in range(int(g["n_markets"])):
+        mk = ctx.market(float(g[f"m{m}_spot"]), float(g["r"]), g[f"m{m}_strike"], g[f"m{m}_maturity"], np.ones(15),
+                        g[f"m{m}_market"])
+        for s in (0, 2):
+            xs, fs = g[f"m{m}_s{s}_xs"], g[f"m{m}_s{s}_fs"]
+            got = mk.loss_batch(xs)
+            assert np.array_equal(got == 1e10, fs == 1e10)
+            err = np.abs(got - fs) / np.maximum(1.0, np.abs(fs))
+            worst = max(worst, err.max())
+            n_eval += fs.size
+        mk.close()
+    print("noisy-market replay: worst abs loss error %.3e over %d reference evaluations" % (worst, n_eval))
+    assert worst <= LOSS_ATOL
+
+
+def _c1_calibrator(cal, gi):
+    opts = [{"strike": float(gi["strike"][j]), "maturity": float(gi["maturity"][j]), "price": float(gi["market"][j]),
+             "option_type": "call"} for j in range(15)]
+    return cal.DoubleHestonJumpCalibrator(float(gi["spot"]), float(gi["r"]), opts)
+
+
+def test_final_loss_reproducible_starts(mods, golden):
+    """Where the reference's optimiser is NOT chaotic its final loss is reproduced to 1e-6 relative: start 0
+    (literature guess) stalls at iteration 0 on the C1 market (f = 9.76104242689233e-05) and on all four noisy
+    markets; the drop-in calibrator must end at the same loss with the same iteration count."""
+    _, cal, _ = mods
+    g = golden("calib_trajectory.npz")
+    c = _c1_calibrator(cal, golden("initial_guess.npz"))
+    res = c.calibrate(maxiter=300, multi_start=1)
+    print("C1 start 0: GPU %.15e (nit %d) vs reference %.15e (nit %d)"
+          % (res.final_loss, res.iterations, float(g["s0_fun"]), int(g["s0_nit"])))
+    assert abs(float(g["s0_fun"]) - 9.76104242689233e-05) <= 1e-18           # SURVEY §7 H1 literal (tripwire)
+    assert abs(res.final_loss - float(g["s0_fun"])) <= FINAL_LOSS_RTOL * float(g["s0_fun"])
+    assert res.iterations == int(g["s0_nit"])
+    gn = golden("calib_noisy.npz")
+    for m in range(int(gn["n_markets"])):
+        opts = [{"strike": float(gn[f"m{m}_strike"][j]), "maturity": float(gn[f"m{m}_maturity"][j]),
+                 "price": float(gn[f"m{m}_market"][j]), "option_type": "call"} for j in range(15)]
+        cm = cal.DoubleHestonJumpCalibrator(float(gn[f"m{m}_spot"]), float(gn["r"]), opts)
+        r0 = cm.calibrate(maxiter=300, multi_start=1)
+        want = float(gn[f"m{m}_s0_fun"])
+        print("noisy market %d start 0: GPU %.12e (nit %d) vs reference %.12e (nit %d)"
+              % (m, r0.final_loss, r0.iterations, want, int(gn[f"m{m}_s0_nit"])))
+        assert abs(r0.final_loss - want) <= FINAL_LOSS_RTOL * want
+        assert r0.iterations == int(gn[f"m{m}_s0_nit"])
+
+
+def test_final_loss_ensemble_two_sided(mods, golden):
+    """Where the reference IS chaotic (start 1 of the C1 run: L-BFGS-B on an h = 1e-8 forward difference branches on
+    1e-16 noise; the reference started from x0 (1 + k 2^-52) ends in three different basins,
+    tests/golden/calib_ensemble.npz) the statement that can hold is distributional and TWO-SIDED: the drop-in, run
+    from the same eight starts, must land in the reference's own basins — not below, not above, and mostly in the
+    same one."""
+    _, cal, _ = mods
+    ens = golden("calib_ensemble.npz")
+    g = golden("calib_trajectory.npz")
+    c = _c1_calibrator(cal, golden("initial_guess.npz"))
+    x0 = g["s1_x0"]
+    got = []
+    for k in ens["k"]:
+        r = c.calibrate(maxiter=300, multi_start=1, x0=(x0 * (1.0 + float(k) * 2.0 ** -52))[None, :])
+        got.append((r.final_loss, r.iterations))
+    fun = np.array([v[0] for v in got])
+    nit = np.array([v[1] for v in got])
+    ref_fun, ref_nit = ens["fun"], ens["nit"]
+    print("reference (fun, nit):", sorted(zip(ref_fun.round(10), ref_nit)))
+    print("GPU       (fun, nit):", sorted(zip(fun.round(10), nit)))
+    # two-sided: inside the reference's spread
+    assert fun.min() >= 0.9 * ref_fun.min() and fun.max() <= 1.1 * ref_fun.max()
+    # every GPU run ends in a basin the reference itself reaches (loss within 10 % of a reference member)
+    in_basin = np.array([(np.abs(ref_fun - f) <= 0.1 * ref_fun).any() for f in fun])
+    assert in_basin.all(), (fun, ref_fun)
+    # the dominant basin is the same (the reference: 5 of 8 at 7.95e-7..7.97e-7, 17 iterations)
+    ref_mode = np.median(ref_fun)
+    assert abs(np.median(fun) - ref_mode) <= 0.1 * ref_mode
+    assert np.median(nit) == np.median(ref_nit)
+
+
+# ---- C5: 10 000 markets x 3 starts -----------------------------------------------------------------------------------
+def test_c5_calibrate_many_10k(mods):
+    """BASELINE configs[4] on one GPU: 10 000 independent multi-start-3 calibrations through calibrate_many; a
+    200-market sub-sample is re-run one market at a time through the drop-in `calibrate` (scipy's L-BFGS-B on the
+    same device loss) from the same starting points."""
+    import dhj
+    _, cal, _ = mods
+    ctx = dhj.default_context()
+    n = 10000
+    lo, hi = O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1]
+    data = ctx.generate(7, 0, n, 500, lo, hi, 0.9, 100.0, 0.0003, 0.01, 0.02, O.GENERATOR_STRIKES_REL,
+                        O.GENERATOR_MATURITIES, 0.03)
+    spots, market = data["spots"], data["market"]
+    K = np.tile(O.GENERATOR_STRIKES_REL[None, :] * spots[:, None] / 100.0, (1, 3))
+    T = np.repeat(O.GENERATOR_MATURITIES, 5)
+    x0 = dhj.initial_guesses(spots, K, T, market, 3)
+    # starts of kind 1 draw from the global RNG: fix them so that the per-market runs below start from the same points
+    t0 = time.perf_counter()
+    res = dhj.calibrate_many(spots, 0.03, K, T, np.ones(15), market, maxiter=300, multi_start=3, x0=x0)
+    wall = time.perf_counter() - t0
+    print(f"C5: {n} markets x 3 starts in {wall:.3f} s ({n / wall:.0f} calibrations/s), {res['rounds']} rounds, "
+          f"median final loss {np.median(res['final_loss']):.3e}")
+    assert res["x"].shape == (n, 13) and np.isfinite(res["final_loss"]).all()
+    # fitted to about the noise level that was added (loss of the true parameters = mean(noise^2) ~ 4e-4)
+    assert np.quantile(res["final_loss"] / data["loss"], 0.99) < 5.0 and (res["final_loss"] < 0.1).all()
+    sub = np.random.default_rng(3).choice(n, size=200, replace=False)
+    single = np.empty(200)
+    for row, i in enumerate(sub):
+        opts = [{"strike": K[i, j], "maturity": T[j], "price": market[i, j], "option_type": "call"} for j in range(15)]
+        c = cal.DoubleHestonJumpCalibrator(spots[i], 0.03, opts)
+        single[row] = c.calibrate(maxiter=300, multi_start=3, x0=x0[i]).final_loss
+    ratio = res["final_loss"][sub] / single
+    print("batched / per-market final-loss ratio over 200 markets: median %.3f, 5%%..95%% %.3f..%.3f, min %.3f max %.3f"
+          % (np.median(ratio), *np.quantile(ratio, [0.05, 0.95]), ratio.min(), ratio.max()))
+    # the two host optimisers (C++ batch, scipy) follow the same algorithm but not the same bits; on a chaotic
+    # objective individual runs differ, the distributions must not
+    assert 0.9 <= np.median(ratio) <= 1.1
+    assert (ratio < 5.0).all() and (ratio > 0.2).all()
+
+
+# ---- C4: the device-resident dataset sweep (counter stream) ----------------------------------------------------------
+GEN = dict(path_len=500, lo=O.GENERATOR_RANGES[:, 0], hi=O.GENERATOR_RANGES[:, 1], persistence=0.9, spot0=100.0,
+           ret_mean=0.0003, ret_sd=0.01, noise_sd=0.02, strikes_rel=O.GENERATOR_STRIKES_REL,
+           maturities=O.GENERATOR_MATURITIES, r=0.03)
+
+
+def test_c4_counter_stream_vs_oracle(ctx):
+    """A range that starts inside a history and crosses two history boundaries: draws (parameters, spots), model
+    prices, market prices and losses against the oracle's restatement of the stream + C pricing."""
+    seed, first, n = 20260104, 300, 1100
+    got = ctx.generate(seed, first, n, **GEN)
+    want = O.counter_generate(seed, first, n, 500)
+    assert np.abs(got["params"] - want["params"]).max() <= 1e-15          # same operations, no libm involved
+    assert rel_err(got["spots"], want["spots"]).max() <= 1e-13            # one log/sqrt/sincos per step of the walk
+    assert got["spots"][200] == 100.0 and got["spots"][700] == 100.0      # samples 500 and 1000 start histories
+    assert rel_err(got["model"], want["model"]).max() <= PRICE_RTOL
+    assert rel_err(got["market"], want["market"]).max() <= PRICE_RTOL
+    assert np.abs(got["loss"] - want["loss"]).max() <= LOSS_ATOL
+    noise = got["market"] / got["model"] - 1.0
+    assert np.abs(noise - want["noise"]).max() <= 1e-13
+    print("counter stream: max rel err model %.2e, market %.2e; max abs err loss %.2e"
+          % (rel_err(got["model"], want["model"]).max(), rel_err(got["market"], want["market"]).max(),
+             np.abs(got["loss"] - want["loss"]).max()))
+
+
+def test_c4_shards_do_not_depend_on_the_split(ctx):
+    """The same 40 000 samples produced in one call, in 3 ragged pieces, and through the device-pointer entry point
+    give the same bits: a shard is a function of (seed, index range) only."""
+    import torch
+    seed, n = 11, 40000
+    whole = ctx.generate(seed, 0, n, **GEN)
+    cuts = [0, 12345, 12345 + 500 * 31, n]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        part = ctx.generate(seed, a, b - a, **GEN)
+        for key in ("params", "spots", "model", "market", "loss"):
+            assert np.array_equal(part[key], whole[key][a:b]), (key, a, b)
+    dev = torch.device("cuda", 0)
+    bufs = {k: torch.empty(s, dtype=torch.float64, device=dev)
+            for k, s in (("params", (n, 13)), ("spots", (n,)), ("model", (n, 15)), ("market", (n, 15)), ("loss", (n,)))}
+    args = [GEN[k] for k in ("path_len", "lo", "hi", "persistence", "spot0", "ret_mean", "ret_sd", "noise_sd",
+                             "strikes_rel", "maturities", "r")]
+    ctx.generate_dev(seed, 0, n, *args, bufs["params"].data_ptr(), bufs["spots"].data_ptr(), bufs["model"].data_ptr(),
+                     bufs["market"].data_ptr(), bufs["loss"].data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for key in bufs:
+        assert np.array_equal(bufs[key].cpu().numpy(), whole[key]), key
+    # sanity of the stream: parameters inside the ranges, noise at its nominal level, histories restart at spot0
+    assert (whole["params"] >= GEN["lo"]).all() and (whole["params"] <= GEN["hi"]).all()
+    assert (whole["spots"][::500] == 100.0).all()
+    assert abs((whole["market"] / whole["model"] - 1.0).std() - 0.02) < 2e-4
+
+
+def test_c4_sharded_generator_api(mods, tmp_path):
+    """generate_synthetic_arrays(seed=..., sharded=True): one process = one shard = the whole dataset; the written
+    shard loads back as a lazy CalibrationResult view with the reference's field layout."""
+    _, _, gen = mods
+    data = gen.generate_synthetic_arrays(1500, seed=5, path_len=500, sharded=True, save_path=tmp_path / "ds")
+    plain = gen.generate_synthetic_arrays(1500, seed=5, path_len=500)
+    for key in ("params", "spots", "model_prices", "market_prices", "losses", "strikes"):
+        assert np.array_equal(data[key], plain[key]), key
+    shards = gen.load_sharded(tmp_path / "ds")
+    assert len(shards) == 1 and len(shards[0]) == 1500
+    item = shards[0][np.int64(501)]                                   # NumPy integer index; second history, step 1
+    assert item.date == "2022-01-04" and item.spot == data["spots"][501]
+    assert item.message == "Synthetic data (not from real calibration)" and item.iterations is None
+    assert np.array_equal(item.market_prices, data["market_prices"][501])
+    want = O.counter_generate(5, 0, 40, 500)
+    assert rel_err(data["model_prices"][:40], want["model"]).max() <= PRICE_RTOL
+
+
+# ---- error recovery of the host-buffer pricing path -------------------------------------------------------------------
+def test_price_host_failure_then_reuse(ctx, monkeypatch):
+    """A call that fails half-way (injected at the third chunk, with staged chunks in flight) must not leave deferred
+    copy-outs behind: the next call on the same context prices correctly and writes only into its own buffer."""
+    import dhj
+    rng = np.random.default_rng(2)
+    P = 700000                                                            # > 5 chunks of 131 072 sets
+    params = rng.uniform(O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1], size=(P, 13))
+    Ks, Ts = O.GENERATOR_STRIKES_REL, O.GENERATOR_MATURITIES
+    good = ctx.price_grid(params, 100.0, Ks, Ts, 0.03)
+    victim = np.full((P, 3, 5), -1.0)
+    monkeypatch.setenv("DHJ_DEBUG_FAIL_AT_CHUNK", "3")
+    with pytest.raises(dhj.NativeError, match="injected failure"):
+        ctx.price_grid(params, 100.0, Ks, Ts, 0.03, out=victim)
+    monkeypatch.delenv("DHJ_DEBUG_FAIL_AT_CHUNK")
+    snapshot = victim.copy()
+    small = ctx.price_grid(params[:1000], 100.0, Ks, Ts, 0.03)
+    assert np.array_equal(small, good[:1000])
+    assert np.array_equal(victim, snapshot)                               # nothing was written into the failed call's buffer
+    assert np.array_equal(ctx.price_grid(params, 100.0, Ks, Ts, 0.03), good)

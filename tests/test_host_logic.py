@@ -186,6 +186,22 @@ def test_flat_dataset_sinks_and_lazy_view(dropins, tmp_path):
         assert [x.spot for x in ds] == list(data["spots"])
         with pytest.raises(IndexError):
             ds[n]
+        # NumPy integer indices (np.random.permutation / np.arange: the usual training access pattern)
+        assert ds[np.int64(5)].spot == r.spot and ds[np.int32(-1)].date == ds[-1].date
+        for idx in np.random.default_rng(0).permutation(n)[:4]:
+            assert ds[idx].spot == data["spots"][idx]
+    # a sliced view written as .npz / directory keeps its offset (dates continue) and indexes with NumPy integers
+    sub = gen.SyntheticCalibrationSet(data)[4:10]
+    sub.save(str(tmp_path / "sub.npz"))
+    sub.save(tmp_path / "sub_dir")
+    for back in (gen.SyntheticCalibrationSet.load(str(tmp_path / "sub.npz")),
+                 gen.SyntheticCalibrationSet.load(tmp_path / "sub_dir")):
+        assert len(back) == 6 and back[np.int64(1)].date == gen._trading_dates(6)[5]
+        assert back[1:][0].spot == data["spots"][5]
+    # counter-stream datasets: the date is the step inside the history
+    hist = dict(data, _first=495, _path_len=500)
+    hs = gen.SyntheticCalibrationSet(hist)
+    assert hs[4].date == gen._trading_dates(500)[499] and hs[5].date == "2022-01-03" and hs[6:][0].date == "2022-01-04"
 
 
 def test_lockstep_evaluator_batches_requests(dropins):

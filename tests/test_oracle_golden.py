@@ -230,3 +230,44 @@ def test_oracle_passes_the_reference_suites_own_checks():
     d = np.array([0.04, 2.0, 0.04, 0.3, -0.5, 0.04, 1.5, 0.04, 0.2, -0.3, 0.5, -0.05, 0.10])
     c, q = O.price_scalar(d, 100, 100, 1.0, 0.05, True), O.price_scalar(d, 100, 100, 1.0, 0.05, False)
     assert abs((c - q) - (100 - 100 * np.exp(-0.05))) < 0.01
+
+
+def test_c_oracle_noisy_trajectories(golden):
+    """Every loss the reference optimiser evaluated on the four noisy markets (tests/golden/calib_noisy.npz, 7 056
+    evaluations incl. sentinel and Feller-active points) from the C restatement; a sub-sample from the scalar port."""
+    g = golden("calib_noisy.npz")
+    total = 0
+    for m in range(int(g["n_markets"])):
+        args = (float(g[f"m{m}_spot"]), float(g["r"]), g[f"m{m}_strike"], g[f"m{m}_maturity"], np.ones(15), g[f"m{m}_market"])
+        for s in (0, 2):
+            xs, fs = g[f"m{m}_s{s}_xs"], g[f"m{m}_s{s}_fs"]
+            got = O.c_loss_batch(xs, *args)
+            assert np.array_equal(got == 1e10, fs == 1e10)
+            assert np.all(np.abs(got - fs) <= 2e-13 * np.maximum(1.0, np.abs(fs)))      # glibc vs npymath, summation order
+            for i in (0, fs.size // 2, fs.size - 1):
+                assert abs(O.loss_scalar(xs[i], *args) - fs[i]) <= 1e-15 * max(1.0, abs(fs[i]))
+            total += fs.size
+    assert total == 7056
+
+
+def test_counter_stream_known_answers():
+    """Philox4x32-10 against the Random123 known-answer vectors (kat_vectors: zero, all-ones and pi-digit inputs),
+    and the structure of the counter stream built on it (the product's definition: csrc/dhj_generate.cuh)."""
+    def kat(ctr, key):
+        return [int(v) for v in O.philox4x32_10(np.array([ctr], dtype=np.uint32), np.array([key], dtype=np.uint32))[0]]
+    assert kat([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert kat([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert kat([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    p, s, nz = O.counter_draws(7, 0, 1200, 500)
+    lo, hi = O.GENERATOR_RANGES[:, 0], O.GENERATOR_RANGES[:, 1]
+    assert (p >= lo).all() and (p <= hi).all()
+    assert s[0] == 100.0 and s[500] == 100.0 and s[1000] == 100.0 and s[499] != 100.0     # histories restart
+    # AR(1) inside a history (synthetic_generator.py:105-109), raw draws at its head
+    raw, _, _ = O.counter_draws(7, 0, 1200, 1)                          # path_len 1: the raw i.i.d. draws
+    assert np.array_equal(p[500], raw[500]) and np.array_equal(p[501], 0.9 * p[500] + (1 - 0.9) * raw[501])
+    # any sub-range reproduces the same values: a function of (seed, index) only
+    p2, s2, n2 = O.counter_draws(7, 700, 100, 500)
+    assert np.array_equal(p2, p[700:800]) and np.array_equal(s2, s[700:800]) and np.array_equal(n2, nz[700:800])
+    big = O.counter_draws(3, 0, 20000, 1)[2]
+    assert abs(big.std() - 0.02) < 3e-4 and abs(big.mean()) < 3e-4
