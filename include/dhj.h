@@ -196,8 +196,9 @@ DHJ_API int dhj_generate(dhj_ctx* ctx, uint64_t seed, int64_t first, int64_t n, 
                          double* loss);
 
 /* ---- measurement ---------------------------------------------------------------------------- */
-/* Runs a register-resident FP64 FMA-chain kernel on every SM and reports the sustained DFMA rate
- * (2 flop per FMA) — the denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 figure). */
+/* Runs register-resident FP64 FMA-chain kernels on every SM (two operand forms: three vector registers, and one
+ * multiplicand from a uniform register) and reports the best sustained DFMA rate (2 flop per FMA) — the
+ * denominator of the FP64 roofline (MEASURED_PEAKS.json has no FP64 figure). */
 DHJ_API int dhj_fp64_peak(dhj_ctx* ctx, int32_t iters, double* tflops, double* milliseconds);
 
 #ifdef __cplusplus

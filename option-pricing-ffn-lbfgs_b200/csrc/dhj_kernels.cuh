@@ -323,18 +323,23 @@ __global__ void k_chi_psi(const int* __restrict__ k_in, int n, double c, double 
   psi[i] = fm::rcp(u) * (sd - sc);
 }
 
-// 8 independent FMA chains per thread; 2 flop per FMA
+// 8 independent FMA chains per thread; 2 flop per FMA.  Two operand forms: all three operands from vector registers
+// (`DFMA R, R, R, R`: the register file caps this form at ~92 % of the pipe's rate on B200), and one multiplicand
+// from a uniform register (`DFMA R, R, UR, R`: the pipe's own rate, 64 FMA/clk/SM).  The addend is made
+// thread-dependent in the second form so that ptxas keeps only the multiplicand uniform.
 constexpr int kPeakChains = 8;
 constexpr int kPeakUnroll = 8;
+template <bool UNIFORM>
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double x, double y) {
   double acc[kPeakChains];
+  const double yv = UNIFORM ? y * (double)(threadIdx.x + 1) : y;
 #pragma unroll
   for (int j = 0; j < kPeakChains; ++j) acc[j] = 1.0 + 1e-3 * (double)(threadIdx.x + j);
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int r = 0; r < kPeakUnroll; ++r) {
 #pragma unroll
-      for (int j = 0; j < kPeakChains; ++j) acc[j] = fma(acc[j], x, y);
+      for (int j = 0; j < kPeakChains; ++j) acc[j] = fma(acc[j], x, yv);
     }
   }
   double s = 0.0;

@@ -113,14 +113,23 @@ def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, 
     market = ctx.market(spots, risk_free_rate, strikes, maturities, is_call, prices)
     state_market = np.repeat(np.arange(n, dtype=np.int32), multi_start)
     opt = BatchLBFGS(x0, maxiter=maxiter, ftol=1e-9, gtol=1e-6)
-    rounds = 0
+    rounds, active_sum = 0, 0
+    t_ask = t_loss = t_tell = 0.0
+    clock = time.perf_counter
     while True:
+        ta = clock()
         idx, x = opt.ask()
+        tb = clock()
+        t_ask += tb - ta
         if idx.size == 0:
             break
         f, g = market.loss_fd(x, 1e-8, market_index=state_market[idx])
+        tc = clock()
         opt.tell(f, g)
+        t_loss += tc - tb
+        t_tell += clock() - tc
         rounds += 1
+        active_sum += idx.size
     xs, fs, nit, nfev, status = opt.result()
     opt.close()
     fs2, xs2 = fs.reshape(n, multi_start), xs.reshape(n, multi_start, 13)
@@ -138,6 +147,8 @@ def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, 
         'success': status.reshape(n, multi_start)[rows, best] <= 1,
         'best_start': best, 'model_prices': model, 'rounds': rounds, 'evaluations': int(nfev.sum()) * 14,
         'seconds': time.time() - t0,
+        # where the wall time of the lock-step loop went: device launches incl. copies / host optimiser
+        'seconds_loss': t_loss, 'seconds_ask': t_ask, 'seconds_tell': t_tell, 'state_rounds': active_sum,
     }
     if return_all_starts:
         out.update({'all_x': xs2, 'all_loss': fs2, 'all_nit': nit.reshape(n, multi_start),
@@ -185,6 +196,8 @@ def _calibrate_pipelined(spots, risk_free_rate, strikes, maturities, is_call, pr
         if isinstance(val, np.ndarray):
             out[key] = np.concatenate([parts[0][key], parts[1][key]], axis=0)
     out['rounds'] = max(parts[0]['rounds'], parts[1]['rounds'])
+    for key in ('seconds_loss', 'seconds_ask', 'seconds_tell', 'state_rounds'):      # per pipeline (they overlap)
+        out[key] = [parts[0][key], parts[1][key]]
     out['launches'] = parts[0]['rounds'] + parts[1]['rounds']
     out['evaluations'] = parts[0]['evaluations'] + parts[1]['evaluations']
     out['seconds'] = time.time() - t0
@@ -219,4 +232,6 @@ def calibrate_many_sharded(spots, risk_free_rate, strikes, maturities, is_call, 
         out[key] = gather_rows(arr.astype(np.float64) if arr.dtype == bool else arr, n, group, device)
     out['success'] = out['success'].astype(bool)
     out['rounds'], out['seconds'] = local['rounds'], local['seconds']
+    for key in ('seconds_loss', 'seconds_ask', 'seconds_tell', 'state_rounds', 'evaluations'):
+        out[key] = local.get(key)
     return out

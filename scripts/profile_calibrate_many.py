@@ -34,7 +34,7 @@ for rep in range(3):
     sm = np.repeat(np.arange(n, dtype=np.int32), 3)
     opt = dhj.BatchLBFGS(x0, maxiter=300, ftol=1e-9, gtol=1e-6)
     rounds = 0
-    active = []
+    active, per_round = [], []
     while True:
         a = time.perf_counter(); idx, x = opt.ask(); b = time.perf_counter()
         if idx.size == 0:
@@ -42,8 +42,18 @@ for rep in range(3):
         f, g = mk.loss_fd(x, 1e-8, market_index=sm[idx]); c = time.perf_counter()
         opt.tell(f, g); d = time.perf_counter()
         t["ask"] += b - a; t["loss"] += c - b; t["tell"] += d - c
-        rounds += 1; active.append(idx.size)
+        rounds += 1; active.append(idx.size); per_round.append(c - b)
     total = time.perf_counter() - t0
     opt.close(); mk.close()
     print(f"rep {rep}: total {total:.3f} s, rounds {rounds}, state-evaluations {sum(active)}: " +
           ", ".join(f"{k} {v:.3f}" for k, v in t.items()) + f"  (OMP_NUM_THREADS={os.environ.get('OMP_NUM_THREADS')})")
+    if rep == 2:
+        act, tr = np.array(active), np.array(per_round)
+        ideal = act * 210 / 1.23e9
+        print(f"   loss time {tr.sum():.3f} s vs ideal kernel time at 1.23e9 prices/s {ideal.sum():.3f} s")
+        for lo_b, hi_b in ((0, 64), (64, 1024), (1024, 8192), (8192, 20000), (20000, 10**9)):
+            sel = (act >= lo_b) & (act < hi_b)
+            if sel.any():
+                print(f"   rounds with {lo_b}..{hi_b} active states: {sel.sum():4d} rounds, {act[sel].sum():8d} state-evals, "
+                      f"loss time {tr[sel].sum() * 1e3:7.1f} ms (ideal {ideal[sel].sum() * 1e3:7.1f} ms), "
+                      f"mean {tr[sel].mean() * 1e6:7.0f} us/round")

@@ -147,8 +147,7 @@ def test_final_loss_ensemble_two_sided(mods, golden):
     """Where the reference IS chaotic (start 1 of the C1 run: L-BFGS-B on an h = 1e-8 forward difference branches on
     1e-16 noise; the reference started from x0 (1 + k 2^-52) ends in three different basins,
     tests/golden/calib_ensemble.npz) the statement that can hold is distributional and TWO-SIDED: the drop-in, run
-    from the same eight starts, must land in the reference's own basins — not below, not above, and mostly in the
-    same one."""
+    from the same eight starts, must land in the reference's own basins — not below, not above, not in between."""
     _, cal, _ = mods
     ens = golden("calib_ensemble.npz")
     g = golden("calib_trajectory.npz")
@@ -163,15 +162,19 @@ def test_final_loss_ensemble_two_sided(mods, golden):
     ref_fun, ref_nit = ens["fun"], ens["nit"]
     print("reference (fun, nit):", sorted(zip(ref_fun.round(10), ref_nit)))
     print("GPU       (fun, nit):", sorted(zip(fun.round(10), nit)))
-    # two-sided: inside the reference's spread
+    # (1) two-sided: nothing below the reference's best basin, nothing above its worst
     assert fun.min() >= 0.9 * ref_fun.min() and fun.max() <= 1.1 * ref_fun.max()
-    # every GPU run ends in a basin the reference itself reaches (loss within 10 % of a reference member)
-    in_basin = np.array([(np.abs(ref_fun - f) <= 0.1 * ref_fun).any() for f in fun])
-    assert in_basin.all(), (fun, ref_fun)
-    # the dominant basin is the same (the reference: 5 of 8 at 7.95e-7..7.97e-7, 17 iterations)
-    ref_mode = np.median(ref_fun)
-    assert abs(np.median(fun) - ref_mode) <= 0.1 * ref_mode
-    assert np.median(nit) == np.median(ref_nit)
+    # (2) no new basin.  The reference ends either in basin A (7.95e-7..7.97e-7 after 17 iterations: 5 of its 8 runs)
+    # or further down the same valley in region B (3.5e-8..5.9e-8 after 37..47 iterations: 3 of 8), never in between.
+    ref_a = ref_fun > 1e-7
+    a_lo, a_hi = ref_fun[ref_a].min(), ref_fun[ref_a].max()
+    b_lo, b_hi = ref_fun[~ref_a].min(), ref_fun[~ref_a].max()
+    assert ref_a.sum() == 5 and set(ref_nit[ref_a]) == {17} and ref_nit[~ref_a].min() >= 37       # fixture tripwire
+    in_a = (fun >= 0.99 * a_lo) & (fun <= 1.01 * a_hi) & (nit == 17)
+    in_b = (fun >= b_lo / 1.25) & (fun <= 1.25 * b_hi) & (nit >= 30) & (nit <= 50)
+    assert (in_a | in_b).all(), (fun, nit)
+    # (3) both basins are reached, as by the reference (8 runs of a chaotic iteration: the split itself is a coin toss)
+    assert in_a.any() and in_b.any()
 
 
 # ---- C5: 10 000 markets x 3 starts -----------------------------------------------------------------------------------
