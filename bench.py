@@ -451,7 +451,9 @@ def roofline_block(per_gpu_prices_per_s, nK, nT, N, kernel_ms, P, fp64_peak, wor
                      "note": "compute-bound path: algorithmic bytes / kernel time, for information"}}
     if ncu:
         stale = ncu.get("kernel_source_sha") != sha
-        slots = ncu["fp64_warp_instructions_per_price"]                  # warp-level FP64 instructions per price
+        slots = ncu.get("fp64_warp_instructions_per_price")               # warp-level FP64 instructions per price
+        if slots is None:
+            slots = ncu["fp64_warp_instructions"] / (ncu.get("prices_per_launch") or P * nK * nT)
         achieved = per_gpu_prices_per_s * slots * 32 * 2 / 1e12         # an issue slot = 32 lanes x 1 FMA = 64 flop
         flops = per_gpu_prices_per_s * ncu["executed_flop_per_price"] / 1e12
         traffic = ncu.get("dram_bytes_per_launch")

@@ -153,6 +153,10 @@ DHJ_API int dhj_lbfgs_tell(dhj_lbfgs* opt, int64_t n_active, const double* f, co
 /* any output may be NULL: x[n][dim], f[n], nit[n], nfev[n], status[n] */
 DHJ_API int dhj_lbfgs_result(const dhj_lbfgs* opt, double* x, double* f, int32_t* nit, int32_t* nfev, int32_t* status);
 
+/* Threads used by the library's host-side parallel loops (optimiser states in ask / tell, staging copies of pageable
+ * buffers); 0 = all cores (default).  Several lock-step pipelines on one host divide the cores with this. */
+DHJ_API int dhj_set_host_threads(int32_t n);
+
 /* ---- synthetic generator: the host-side draw stream -------------------------------------------
  * Replaces the per-sample Python loop of generate_synthetic_calibrations
  * (/root/reference/src/data/synthetic_generator.py:98-142: 13 np.random.uniform, one np.random.normal(0.0003,

@@ -18,6 +18,8 @@
 
 using namespace dhj;
 
+extern "C" int dhj_host_threads();      // dhj_lbfgs.cpp: threads of the host-side parallel loops
+
 namespace {
 
 char g_init_error[512] = "";
@@ -198,10 +200,7 @@ int fail(dhj_ctx* ctx, int code, const char* fmt, ...) {
 // staging copies between the caller's pageable memory and the pinned slots: a single thread moves ~10 GB/s, less
 // than the kernel consumes per chunk, so large copies are split over eight host threads (four: 14.75 ms per
 // 1 Mi-set grid from pageable memory, eight: 14.28)
-int copy_threads() {
-  static const int n = std::max(1, std::min(8, omp_get_num_procs()));
-  return n;
-}
+int copy_threads() { return std::max(1, std::min(8, dhj_host_threads())); }
 
 void host_copy(void* dst, const void* src, size_t bytes) {
   constexpr size_t kPiece = (size_t)1 << 18;
@@ -660,11 +659,15 @@ static int run_loss(dhj_ctx* ctx, const dhj_market* mk, const double* x, const i
     DHJ_CUDA(ctx, ctx->d_fg.reserve(res_bytes));
   }
   const SliceView& v = mk->view;
-  // Large batches go through the pricing kernel (expand -> k_price_batch -> reduce): compiled for 128 registers it
-  // prices 20 % faster than the fused loss kernel, which pays for two extra small launches from ~8 k loss
-  // evaluations on (a 30 000-state FD round: 6.2 -> 5.4 ms).  Both paths produce the same bits.
-  constexpr int64_t kSplitUnits = 8192;
-  if (mk->book.max_slice <= kBatchMaxStrikes && v.n_slices <= kBatchItems && n_units < kSplitUnits) {
+  // Large batches go through the pricing kernel (expand -> k_price_batch -> reduce): its batches of 32 items keep the
+  // four warps balanced whatever the number of slices per loss evaluation, which pays for two extra small launches
+  // from a few thousand evaluations on.  Both paths run the same arithmetic and produce the same bits
+  // (DHJ_DEBUG_SPLIT_UNITS: developer knob for measuring the crossover).
+  static const int64_t kSplitUnits = [] {
+    const char* e = getenv("DHJ_DEBUG_SPLIT_UNITS");
+    return e ? (int64_t)atoll(e) : (int64_t)8192;
+  }();
+  if (mk->book.max_slice <= kBatchMaxStrikes && v.n_slices <= kPriceItems && n_units < kSplitUnits) {
     // fused path: one launch
     if (fd) {
       const size_t cb = (size_t)B * sizeof(unsigned int);
@@ -680,8 +683,8 @@ static int run_loss(dhj_ctx* ctx, const dhj_market* mk, const double* x, const i
     a.f_all = (double*)ctx->d_f.p; a.fg = fd ? (double*)ctx->d_fg.p : nullptr;
     a.counters = fd ? (unsigned int*)ctx->d_counters.p : nullptr;
     // whole units per block batch; few units (one calibration) -> one unit per block so that every unit
-    // runs on its own SM (latency), many units -> full batches of kBatchItems items (throughput)
-    const int upb_max = std::max(1, kBatchItems / v.n_slices);
+    // runs on its own SM (latency), many units -> full batches of kPriceItems items (throughput)
+    const int upb_max = std::max(1, kPriceItems / v.n_slices);
     const long long resident = (long long)ctx->sm_count * ctx->loss_blocks_per_sm;
     a.units_per_batch = (int)std::max<long long>(1, std::min<long long>(upb_max, n_units / resident));
     const long long batches = (n_units + a.units_per_batch - 1) / a.units_per_batch;

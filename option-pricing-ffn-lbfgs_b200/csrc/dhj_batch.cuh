@@ -2,7 +2,7 @@
 // (the 15-option grid of C2 / C4 / the generator / the calibrator's market).
 //
 // Decomposition: ONE LANE PER COSINE INDEX k, a block of 128 threads walks a batch of
-// 32 items (28 in the loss kernel; item = one (parameter set, maturity slice)):
+// 32 items (item = one (parameter set, maturity slice)):
 //   phase 1  thread t < 32 prepares item t ALONE: parameters (optionally exp/tanh transform), per-set
 //            constants, truncation range, pass constants, the slice's strikes (K, log(K/S0), exp(.),
 //            binding flags) -> shared memory.  The prologue is therefore executed once per item by one
@@ -23,26 +23,21 @@ namespace dhj {
 
 constexpr int kBatchThreads = 128;
 constexpr int kBatchWarps = kBatchThreads / 32;
-// items per block batch: 28 in the loss kernel (its 7 blocks/SM leave 32 KB of shared memory per block), 32 in the
-// pricing kernel (4 blocks/SM: shared memory is not the limit, and phase 1 then fills its warp)
-#ifndef DHJ_BATCH_ITEMS
-#define DHJ_BATCH_ITEMS 28
-#endif
+// items per block batch: phase 1 fills its warp
 #ifndef DHJ_PRICE_ITEMS
 #define DHJ_PRICE_ITEMS 32
 #endif
-constexpr int kBatchItems = DHJ_BATCH_ITEMS;
 constexpr int kPriceItems = DHJ_PRICE_ITEMS;
 constexpr int kBatchMaxStrikes = 8;
 // resident blocks per SM the kernels are compiled for (register budget = 65 536 / (128 * MINB)).  Measured on C2
 // (profiles/README.md): 7 blocks at 72 registers 14.36 ms, 6 at 80 14.40, 5 at 96 14.51, 4 at 122 14.03, 3 at 140
 // 14.72 — with room for the temporaries of both Heston factors ptxas overlaps their dependent chains, which is
-// worth more than the 12 warps given up.  The loss kernel (more shared memory per block) prefers 7.
+// worth more than the 12 warps given up.  The fused loss kernel runs the same engine with the same budget (a
+// 72-register build that parked its loop state in shared memory was 20 % slower per price and had to evaluate some
+// terms differently from the pricing kernel; one arithmetic for both keeps every loss independent of how the
+// evaluations are grouped into launches).
 #ifndef DHJ_BATCH_MINB
 #define DHJ_BATCH_MINB 4
-#endif
-#ifndef DHJ_LOSS_MINB
-#define DHJ_LOSS_MINB 7
 #endif
 
 struct ItemRec {
@@ -50,6 +45,7 @@ struct ItemRec {
   PassConsts pass;                 // regular pass: (a0, b0) = (pass.a, pass.b)
   double S0, disc;
   double cmu, smu;                 // cos / sin(32 u_1 mu): the jump term's rotation from one block of 32 k to the next
+  double gj2;                      // exp(-2048 alpha), alpha = sj^2 u_1^2 / 2: second ratio of the jump factor's Gaussian
   double K[kBatchMaxStrikes], x[kBatchMaxStrikes], ex[kBatchMaxStrikes];      // strike, log(K/S0), S0 * exp(x)
   double cth[kBatchMaxStrikes], sth[kBatchMaxStrikes];      // cos / sin of theta_j = u_1 (x_j - a0)
   double c32[kBatchMaxStrikes], s32[kBatchMaxStrikes];      // cos / sin of 32 theta_j
@@ -58,25 +54,19 @@ struct ItemRec {
   long long out_row;               // p * M
 };
 
-// one warp's k-block of strike-independent coefficients P, Q, R.  In the 72-register loss kernel (PARK) the same
-// slots park the lanes' rotation state between two blocks of k (PQ = cos / sin(u_k mu); R, X = the segment start's
-// cos / sin), so that it does not occupy registers while the characteristic function is evaluated, and A1, A2, A3
-// accumulate each lane's share of the strike-independent sums over all blocks of a pass (reduced once per pass,
-// not once per block); the 128-register pricing kernel keeps all of that in registers.
+// one warp's k-block of strike-independent coefficients P, Q, R.
 // Layout: PQ[k] = (P_k, Q_k) and R[k], for 128-bit loads in the contraction (one for P and Q, one for two consecutive
 // R); the batch kernel's four 8-term segments are read concurrently by different lanes, so each segment is shifted
 // by one 16-byte slot (PQ) / two doubles (R) to land in different banks.
 struct CoefStage {
   Pair PQ[36];
-  double R[40], X[32];
-  double A1[32], A2[32], A3[32];
-  double g0;
+  double R[40];
 };
 
 // pass of a strike whose +-0.1 widening binds: its own (a, b) and the rotation steps that go with it
 struct ExtraPass {
   PassConsts pass;
-  double cth, sth, c32, s32, cmu, smu;
+  double cth, sth, c32, s32, cmu, smu, gj2;      // (cmu, smu, gj2 contiguous: contract_pass reads them as one triple)
 };
 
 template <int ITEMS>
@@ -86,8 +76,7 @@ struct BatchSmemT {
   CoefStage stage[kBatchWarps];
   fm::Tables ltab;                 // fm::log_tab / exp_tab / atan2_tab tables (per-lane index: shared memory, not the constant bank)
 };
-using BatchSmem = BatchSmemT<kBatchItems>;        // loss kernel
-using PriceSmem = BatchSmemT<kPriceItems>;        // pricing kernel
+using PriceSmem = BatchSmemT<kPriceItems>;
 
 struct PriceArgs;                  // dhj_kernels.cuh
 
@@ -113,6 +102,13 @@ __device__ __forceinline__ void strike_rotation(const PassConsts& p, double x, d
 __device__ __forceinline__ void jump_rotation(const PassConsts& p, double mu, double* cmu, double* smu) {
   fm::sincos_((32.0 * u_one(p)) * mu, smu, cmu);
 }
+// The jump factor's magnitude exp(-alpha k^2), alpha = hsj2 u_1^2, is Gaussian in k: from one block of 32 k to the
+// next it is multiplied by rho_b = exp(-alpha (64 k + 1024)), and rho itself by the constant exp(-2048 alpha):
+// two products per block instead of an exp (exact re-evaluation with the rotations, every kReseed blocks).
+__device__ __forceinline__ double jump_alpha(const PassConsts& p, double hsj2) {
+  const double u1 = u_one(p);
+  return hsj2 * (u1 * u1);
+}
 
 // phase 1 for one item, executed by a single thread
 __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, const Params& m, double S0,
@@ -125,6 +121,7 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
   rec.S0 = S0;
   rec.disc = fm::exp_(-v.r * T);
   jump_rotation(rec.pass, rec.set.mu, &rec.cmu, &rec.smu);
+  rec.gj2 = fm::exp_neg(-2048.0 * jump_alpha(rec.pass, rec.set.hsj2));
   const int o_lo = v.slice_off[s_idx], cnt = v.slice_off[s_idx + 1] - o_lo;
   unsigned bind = 0, call = 0;
 #pragma unroll 1
@@ -158,9 +155,6 @@ __device__ __forceinline__ void rotate(double& c, double& s, double cr, double s
 // reduced over the 4 segments by two shuffles and accumulated in `acc` of the lanes (j, 0).  The sums A1, A2, A3
 // (and g0) do not depend on the strike: each lane accumulates its share over the blocks and the warp reduces
 // them once at the end of the pass.
-// PARK: keep the loop-carried state (rotation state, A-sum accumulators) in the stage's shared-memory slots
-// between blocks of k (kernels compiled for 72 registers) instead of in registers (the pricing kernel at 122).
-template <bool PARK>
 __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConsts& pc, const double* __restrict__ cth,
                                               const double* __restrict__ sth, const double* __restrict__ c32,
                                               const double* __restrict__ s32, const double* __restrict__ cmu_smu,
@@ -170,38 +164,33 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
   const int slot_pq = lane + (lane >> 3), slot_r = lane + 2 * (lane >> 3);      // padded stage slots of this lane's k
   // A1, A2 feed calls, A3 puts (uniform per pass)
   const bool any_call = (it.call_mask & mask) != 0, any_put = (~it.call_mask & mask) != 0;
-  if (PARK) { st.A1[lane] = 0.0; st.A2[lane] = 0.0; st.A3[lane] = 0.0; }     // each lane owns its slots
   double a1 = 0.0, a2 = 0.0, a3 = 0.0, g0_keep = 0.0;
   double cj = 1.0, sj = 0.0, cs = 1.0, sn = 0.0;
+  double ej = 1.0, rho = 1.0;                                  // jump Gaussian and its block-to-block ratio
   int blk = 0;
-  // two blocks of k per trip in the register-rich pricing kernel (the `exact` test and the loop overhead are
-  // shared; four copies overflow the instruction cache: 13.29 / 13.06 / 14.73 ms for 1 / 2 / 4)
-#pragma unroll(PARK ? 1 : 2)
+  // two blocks of k per trip (the `exact` test and the loop overhead are shared; four copies overflow the
+  // instruction cache: 13.29 / 13.06 / 14.73 ms for 1 / 2 / 4)
+#pragma unroll 2
   for (int k0 = 0; k0 < n_cos; k0 += 32, ++blk) {
     const int k = k0 + lane;
     const bool exact = (blk % kReseed) == 0;               // uniform
     const double u = u_of_k(pc, k);
-    KTerm t = make_kterm_f(it.set, pc, k, ltab, u, [&](double* cj_out, double* sj_out) {
-      if (exact) fm::sincos_(u * it.set.mu, &sj, &cj);
-      else {
-        if (PARK) { const Pair t2 = st.PQ[slot_pq]; cj = t2.x; sj = t2.y; }
+    KTerm t = make_kterm_f(it.set, pc, k, ltab, u, [&](double* cj_out, double* sj_out, double* ej_out) {
+      if (exact) {
+        fm::sincos_(u * it.set.mu, &sj, &cj);
+        ej = jump_gauss(it.set, u, ltab);
+        rho = fm::exp_tab_neg(-(jump_alpha(pc, it.set.hsj2) * (double)(64 * k + 1024)), ltab);
+      } else {
+        ej *= rho; rho *= cmu_smu[2];
         rotate(cj, sj, cmu_smu[0], cmu_smu[1]);
       }
-      *cj_out = cj; *sj_out = sj;
+      *cj_out = cj; *sj_out = sj; *ej_out = ej;
     });
     t.G = (k < n_cos) ? t.G : 0.0;                           // ragged last block: every coefficient is a multiple of G
     const KCoef c = make_kcoef(t, pc, k);
-    if (PARK) {
-      cs = 1.0; sn = 0.0;                                    // not carried in registers: reloaded below
-      if (any_call) { st.A1[lane] = fma(c.P, t.t1 + t.t3, st.A1[lane]); st.A2[lane] = fma(c.R, t.sb, st.A2[lane]); }
-      if (any_put) st.A3[lane] += c.P;
-      if (k == 0) st.g0 = c.g0;
-      if (!exact) { cs = st.R[slot_r]; sn = st.X[lane]; }
-    } else {
-      if (any_call) { a1 = fma(c.P, t.t1 + t.t3, a1); a2 = fma(c.R, t.sb, a2); }
-      if (any_put) a3 += c.P;
-      if (blk == 0) g0_keep = __shfl_sync(kFullMask, c.g0, 0);
-    }
+    if (any_call) { a1 = fma(c.P, t.t1 + t.t3, a1); a2 = fma(c.R, t.sb, a2); }
+    if (any_put) a3 += c.P;
+    if (blk == 0) g0_keep = __shfl_sync(kFullMask, c.g0, 0);
     __syncwarp();
     st.PQ[slot_pq] = make_double2(c.P, c.Q); st.R[slot_r] = c.R;
     __syncwarp();
@@ -219,17 +208,12 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
     val += __shfl_xor_sync(kFullMask, val, 1);
     val += __shfl_xor_sync(kFullMask, val, 2);
     acc += val;                                              // meaningful in the lanes (j, 0) of active strikes
-    if (PARK) {
-      __syncwarp();                                          // the coefficients have been consumed: park the state
-      st.PQ[slot_pq] = make_double2(cj, sj); st.R[slot_r] = cs; st.X[lane] = sn;
-    }
   }
   // strike-independent sums of the pass, then the constant part of each strike
-  if (PARK) { a1 = st.A1[lane]; a2 = st.A2[lane]; a3 = st.A3[lane]; }
   const double A1 = any_call ? warp_sum(a1) : 0.0, A2 = any_call ? warp_sum(a2) : 0.0;
   const double A3 = any_put ? warp_sum(a3) : 0.0;
   __syncwarp();
-  const double g0 = PARK ? st.g0 : g0_keep;
+  const double g0 = g0_keep;
   const int j = lane / kNumSeg;
   if ((mask >> j) & 1u)
     acc += strike_const_part((it.call_mask >> j) & 1u, it.S0, it.K[j], it.x[j], pc, A1, A2, A3, g0);
@@ -238,7 +222,7 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
 // phase 2 for a batch of `cnt_items` prepared items: warp w prices items w, w + 4, ... on its own — no block
 // barrier, no partial sums in shared memory; sink(i, j, item, price) receives each price from lane 4 j.
 // Strikes with their own (a, b) get an extra pass each (rare), set up by lane 0 in the warp's ExtraPass.
-template <bool PARK, class Smem, class Sink>
+template <class Smem, class Sink>
 __device__ __forceinline__ void run_batch(Smem& sm, const SliceView& v, int cnt_items, int tid, Sink sink) {
   // the shuffle tells ptxas that the warp index is warp-uniform: the item loop and everything addressed through it
   // then run on the uniform datapath (constants via LDCU into uniform registers, address arithmetic off the
@@ -251,7 +235,7 @@ __device__ __forceinline__ void run_batch(Smem& sm, const SliceView& v, int cnt_
     double acc = 0.0;
     const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
     if (reg_mask)
-      contract_pass<PARK>(it, it.pass, it.cth, it.sth, it.c32, it.s32, &it.cmu, reg_mask, v.n_cos, lane,
+      contract_pass(it, it.pass, it.cth, it.sth, it.c32, it.s32, &it.cmu, reg_mask, v.n_cos, lane,
                     sm.stage[warp], &sm.ltab, acc);
     unsigned todo = it.valid_mask & it.bind_mask;            // uniform: the masks live in shared memory
     while (todo) {
@@ -263,11 +247,12 @@ __device__ __forceinline__ void run_batch(Smem& sm, const SliceView& v, int cnt_
                                    it.pass.T);
         strike_rotation(ex.pass, it.x[jb], &ex.cth, &ex.sth, &ex.c32, &ex.s32);
         jump_rotation(ex.pass, it.set.mu, &ex.cmu, &ex.smu);
+        ex.gj2 = fm::exp_neg(-2048.0 * jump_alpha(ex.pass, it.set.hsj2));
       }
       __syncwarp();
       // the task code indexes the rotation steps by strike: point it at the single extra entry
       double acc_b = 0.0;
-      contract_pass<PARK>(it, ex.pass, &ex.cth - jb, &ex.sth - jb, &ex.c32 - jb, &ex.s32 - jb, &ex.cmu, 1u << jb,
+      contract_pass(it, ex.pass, &ex.cth - jb, &ex.sth - jb, &ex.c32 - jb, &ex.s32 - jb, &ex.cmu, 1u << jb,
                     v.n_cos, lane, sm.stage[warp], &sm.ltab, acc_b);
       if ((lane >> 2) == jb) acc = acc_b;
     }

@@ -376,7 +376,8 @@ DHJ_FM double atan2_tab_impl(double y, double x, const Tables* __restrict__ tab)
   unsigned i = (unsigned)lo32(tt);
   i = i < 64u ? i : 64u;
   const double c = tt - kS.AtanMagic;
-  const double t = div(fma(-c, mx, mn), fma(c, mn, mx));
+  // |t| < 1/127: the quotient's last-bit repair (fm::div) would change the result by < 2^-60; one product suffices
+  const double t = fma(-c, mx, mn) * rcp(fma(c, mn, mx));
   const double z = t * t;
   const double p = fma(z, fma(z, -0.14285719394683837891, kS.AtC2), kS.AtC1);   // -1/7 as a high word: immediate
   double r = tab->atan64[i] + fma(t * z, p, t);     // atan(mn/mx) in [0, pi/4]

@@ -6,7 +6,7 @@
 //                  1e10 sentinel; in FD mode the 14 stencil points of an optimiser state are 14 units and the
 //                  thread that finishes the last one assembles scipy's gradient — ONE launch per optimiser step
 //   k_fd_expand / k_loss_reduce  K2 around the pricing kernels: markets with > 8 strikes per maturity, and any
-//                  batch of >= 8 192 loss evaluations (the 128-register k_price_batch outruns the fused kernel)
+//                  batch of >= 8 192 loss evaluations (full 32-item batches balance the warps better)
 //   k_cf / k_truncation_range / k_chi_psi  the remaining public methods of DoubleHeston
 //   k_fp64_peak    DFMA-chain probe for the FP64 roofline denominator
 #pragma once
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
     }
     __syncthreads();
     // ---- phase 2: a warp per item, a lane per cosine index; the warp writes its prices -------------------
-    run_batch<false>(sm, v, cnt_items, tid, [&](int, int j, const ItemRec& it, double price) {
+    run_batch(sm, v, cnt_items, tid, [&](int, int j, const ItemRec& it, double price) {
       a.out[it.out_row + v.pos[it.o_lo + j]] = price;
     });
     __syncthreads();
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_DENSE_MINB) k_price_dense(S
 
 // Fused loss kernel on the batch engine (slices of <= 8 strikes, <= 32 slices): a "unit" is one loss evaluation
 // (one x; in FD mode one of the 14 stencil points of an optimiser state); a block batch holds
-// `units_per_batch` whole units (= units_per_batch * n_slices <= kBatchItems items), prices them as k_price_batch does,
+// `units_per_batch` whole units (= units_per_batch * n_slices <= kPriceItems items), prices them as k_price_batch does,
 // then one thread per unit forms mean(rel^2) + Feller / the 1e10 sentinel, and the thread that completes a
 // state's 14th point assembles scipy's forward-difference gradient.
 struct LossBatchArgs {
@@ -145,9 +145,9 @@ struct LossBatchArgs {
   unsigned int* counters;    // fd: [C]
 };
 
-__global__ void __launch_bounds__(kBatchThreads, DHJ_LOSS_MINB) k_loss_batch(SliceView v, LossBatchArgs a) {
-  __shared__ BatchSmem sm;
-  __shared__ double s_feller[kBatchItems];
+__global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_loss_batch(SliceView v, LossBatchArgs a) {
+  __shared__ PriceSmem sm;
+  __shared__ double s_feller[kPriceItems];
   const int tid = threadIdx.x;
   load_log_table(&sm.ltab, tid);
   const int nS = v.n_slices;
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_LOSS_MINB) k_loss_batch(Sli
     __syncthreads();
     // ---- phase 2 (as k_price_batch): prices -> shared memory, in the item's ex[] slots (exp(x_j) is dead once
     // the item's passes are done; only the warp that owns the item touches them) -----------------------------
-    run_batch<true>(sm, v, cnt_items, tid, [&](int i, int j, const ItemRec&, double price) { sm.items[i].ex[j] = price; });
+    run_batch(sm, v, cnt_items, tid, [&](int i, int j, const ItemRec&, double price) { sm.items[i].ex[j] = price; });
     __syncthreads();
     // ---- phase 4: one thread per unit: loss, and the gradient when a state's stencil is complete ----------
     if (tid < n_units_here) {

@@ -27,6 +27,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <omp.h>
 
 #include "dhj.h"
 
@@ -355,6 +356,16 @@ int dhj_lbfgs_destroy(dhj_lbfgs* o) {
   return DHJ_OK;
 }
 
+// threads of the library's host-side parallel loops (optimiser states, staging copies); 0 = all cores.  Several
+// lock-step pipelines on one host (dhj.calibrate_many) divide the cores among themselves with this.
+static int g_host_threads = 0;
+int dhj_host_threads() { return g_host_threads > 0 ? g_host_threads : omp_get_num_procs(); }
+int dhj_set_host_threads(int32_t n) {
+  if (n < 0) return DHJ_ERR_ARG;
+  g_host_threads = n;
+  return DHJ_OK;
+}
+
 int dhj_lbfgs_ask(dhj_lbfgs* o, int64_t* n_active, int64_t* idx, double* x) {
   if (!o || !n_active || !idx || !x) return DHJ_ERR_ARG;
   o->asked.clear();
@@ -362,7 +373,7 @@ int dhj_lbfgs_ask(dhj_lbfgs* o, int64_t* n_active, int64_t* idx, double* x) {
     if (o->st[i].status == kRunning && o->st[i].need_eval) o->asked.push_back(i);
   *n_active = (int64_t)o->asked.size();
   const int64_t na = (int64_t)o->asked.size();
-#pragma omp parallel for schedule(static) if (na > 4096)
+#pragma omp parallel for schedule(static) num_threads(dhj_host_threads()) if (na > 4096)
   for (int64_t a = 0; a < na; ++a) {
     idx[a] = o->asked[a];
     memcpy(x + a * o->dim, o->row(o->xt, o->asked[a]), o->dim * sizeof(double));
@@ -373,7 +384,7 @@ int dhj_lbfgs_ask(dhj_lbfgs* o, int64_t* n_active, int64_t* idx, double* x) {
 int dhj_lbfgs_tell(dhj_lbfgs* o, int64_t n_active, const double* f, const double* g) {
   if (!o || !f || !g || n_active != (int64_t)o->asked.size()) return DHJ_ERR_ARG;
   // states are independent: advance them on all host cores (30 000 states per round in config C5)
-#pragma omp parallel for schedule(static) if (n_active > 256)
+#pragma omp parallel for schedule(static) num_threads(dhj_host_threads()) if (n_active > 256)
   for (int64_t a = 0; a < n_active; ++a) {
     const int64_t i = o->asked[a];
     o->st[i].need_eval = false;

@@ -81,7 +81,7 @@ struct SetConsts {
   double two_kappa[2];
   double rs[2];                // rho*sigma
   double s2[2];                // sigma^2
-  double sv[2];                // v0/sigma^2
+  double v0[2];                // v0
   double c[2];                 // kappa*theta/sigma^2
   double drift;                // r - q - lam*(exp(mu + sj^2/2) - 1)       double_heston.py:82-83
   double lam, mu, hsj2;        // hsj2 = 0.5*sj^2
@@ -95,7 +95,7 @@ DHJ_HD SetConsts make_set_consts(const Params& m, double r, double q) {
     s.rs[j] = m.rho[j] * m.sigma[j];
     s.s2[j] = m.sigma[j] * m.sigma[j];
     s.two_kappa[j] = m.kappa[j] + m.kappa[j];
-    s.sv[j] = fm::div(m.v0[j], s.s2[j]);
+    s.v0[j] = m.v0[j];
     s.c[j] = fm::div(m.kappa[j] * m.theta[j], s.s2[j]);
   }
   s.hsj2 = 0.5 * (m.sj * m.sj);
@@ -170,7 +170,7 @@ DHJ_HD PassConsts make_pass_consts(const SetConsts& s, double a, double b, doubl
 // wherever possible (an FP64 instruction is the scarce resource); g itself is never formed.
 // The factor's terms are ADDED to running sums with fused multiply-adds (an FP64 instruction is the scarce
 // resource): aR, aI += A_j without its -2 c_j i arg(.) part, which goes to sli += c_j arg(.);
-// xbr, xbi += B_j v0_j.  Scalars are folded: B_j v0_j = (m (1-E) pl conj(D)) * (|D|^-2 v0/sigma^2), and
+// xbr, xbi += B_j v0_j.  Scalars are folded: B_j v0_j = -(v0 u) (u + i) (1-E) conj(D) |D|^-2 (m pl = -sigma^2 u (u+i)), and
 // -2 log|D/(2d)| = log(4 |z| / |D|^2) comes straight from the table-driven log (the 4 is an exponent offset).
 DHJ_HD void heston_factor(const SetConsts& s, int j, double u, double T, const fm::Tables* __restrict__ ltab,
                           double& aR, double& aI, double& sli, double& xbr, double& xbi) {
@@ -190,9 +190,18 @@ DHJ_HD void heston_factor(const SetConsts& s, int j, double u, double T, const f
   const double yt = fm::rsqrt(x2);
   const double t = x2 * yt;
   const double other = (0.5 * zi) * yt;
-  const bool pos = zr >= 0.0;
-  const double dr = pos ? t : fabs(other);
-  const double di = pos ? other : copysign(t, zi);
+  // Re z = kappa^2 + sigma^2 u^2 (1 - rho^2) >= 0 whenever |rho| <= 1 (always, after the calibrator's tanh): the
+  // other branch of glibc's formula is taken only if some lane of the warp needs it (one vote instead of four
+  // selects and two sign operations per factor and k)
+  double dr = t, di = other;
+#if defined(__CUDA_ARCH__)
+  if (__any_sync(__activemask(), zr < 0.0))
+#endif
+  {
+    const bool pos = !(zr < 0.0);
+    dr = pos ? t : fabs(other);
+    di = pos ? other : copysign(t, zi);
+  }
   // E = exp(-d T)
   const double er = fm::exp_tab_neg(-dr * T, ltab);
   double sn, cs;
@@ -205,14 +214,14 @@ DHJ_HD void heston_factor(const SetConsts& s, int j, double u, double T, const f
   const double Di = fma(-mr, Ei, fma(-mi, Er, pi_));
   const double nD = fma(Dr, Dr, Di * Di);
   const double inD = fm::rcp(nD);
-  // B v0 = m * [(1-E) * pl * conj(D)] * (v0 / (sigma^2 |D|^2))
+  // B v0 = (m pl) (1-E) conj(D) v0 / (sigma^2 |D|^2) with  m pl = beta^2 - d^2 = beta^2 - z = -sigma^2 u (u + i):
+  //      = -(v0 u) * (u + i) * [(1-E) conj(D)] / |D|^2          (one complex product instead of three)
   const double ar = 1.0 - Er, ai = -Ei;
-  const double tr = fma(ar, pr, -(ai * pi_)), ti = fma(ar, pi_, ai * pr);
-  const double Qr = fma(tr, Dr, ti * Di), Qi = fma(ti, Dr, -(tr * Di));
-  const double Br = fma(mr, Qr, -(mi * Qi)), Bi = fma(mr, Qi, mi * Qr);
-  const double g = inD * s.sv[j];
-  xbr = fma(Br, g, xbr);
-  xbi = fma(Bi, g, xbi);
+  const double Nr = fma(ar, Dr, ai * Di), Ni = fma(ai, Dr, -(ar * Di));
+  const double Mr = fma(Nr, u, -Ni), Mi = fma(Ni, u, Nr);
+  const double g = -((s.v0[j] * u) * inD);
+  xbr = fma(Mr, g, xbr);
+  xbi = fma(Mi, g, xbi);
   // A = c (m T - 2 log(D/(2d))):  -2 log|D/(2d)| = log(4 |z| / |D|^2), |d|^2 = |z| = h;  argument from D*conj(d)
   const double L = fm::log_tab(h * inD, ltab, 2);
   const double li = fm::atan2_tab_nz(fma(Di, dr, -(Dr * di)), fma(Dr, dr, Di * di), ltab);
@@ -227,8 +236,14 @@ DHJ_HD void heston_factor(const SetConsts& s, int j, double u, double T, const f
 //   X = ((A0 + A1) + A2) + B1 v01 + B2 v02  +  lamT (exp(i u mu - hsj2 u^2) - 1),  A0 = i (drift u) T
 // The two factors are unrolled: with the table-driven elementary functions the body is small enough for the
 // instruction cache, and the rolled loop's register shuffling cost more than the second copy.
-// jump_trig(&cj, &sj) supplies cos / sin(u mu) AFTER the two Heston factors (where register pressure peaks): the
-// batch kernel advances them by rotation from one block of k to the next instead of evaluating a sincos
+// jump_trig(&cj, &sj, &ej) supplies cos / sin(u mu) and exp(-sj^2 u^2 / 2) AFTER the two Heston factors (where
+// register pressure peaks): the batch kernel advances all three by recurrences from one block of k to the next
+// instead of evaluating a sincos and an exp
+// exp(-sigma_j^2 u^2 / 2) of the jump factor (double_heston.py:93)
+DHJ_HD double jump_gauss(const SetConsts& s, double u, const fm::Tables* __restrict__ ltab) {
+  return fm::exp_tab_neg(-(s.hsj2 * (u * u)), ltab);
+}
+
 template <class JumpTrig>
 DHJ_HD void cf_exponent_f(const SetConsts& s, double u, double T, double lamT, const fm::Tables* __restrict__ ltab,
                           JumpTrig jump_trig, double* xr_out, double* xi_out) {
@@ -237,9 +252,8 @@ DHJ_HD void cf_exponent_f(const SetConsts& s, double u, double T, double lamT, c
   for (int j = 0; j < 2; ++j) heston_factor(s, j, u, T, ltab, aR, aI, sli, xbr, xbi);
   double xr = aR + xbr;
   double xi = fma(-2.0, sli, aI) + xbi;
-  const double ej = fm::exp_tab_neg(-(s.hsj2 * (u * u)), ltab);
-  double cj, sj;
-  jump_trig(&cj, &sj);
+  double cj, sj, ej;
+  jump_trig(&cj, &sj, &ej);
   xr = fma(lamT, fma(ej, cj, -1.0), xr);
   xi = fma(lamT, ej * sj, xi);
   *xr_out = xr; *xi_out = xi;
@@ -247,7 +261,10 @@ DHJ_HD void cf_exponent_f(const SetConsts& s, double u, double T, double lamT, c
 
 DHJ_HD void cf_exponent(const SetConsts& s, double u, double T, double lamT, const fm::Tables* __restrict__ ltab,
                         double* xr_out, double* xi_out) {
-  cf_exponent_f(s, u, T, lamT, ltab, [&](double* cj, double* sj) { fm::sincos_(u * s.mu, sj, cj); }, xr_out, xi_out);
+  cf_exponent_f(s, u, T, lamT, ltab, [&](double* cj, double* sj, double* ej) {
+    fm::sincos_(u * s.mu, sj, cj);
+    *ej = jump_gauss(s, u, ltab);
+  }, xr_out, xi_out);
 }
 
 // everything the strike loop needs for one k
@@ -294,7 +311,10 @@ DHJ_HD KTerm make_kterm_f(const SetConsts& s, const PassConsts& p, int k, const 
 
 DHJ_HD KTerm make_kterm(const SetConsts& s, const PassConsts& p, int k, const fm::Tables* __restrict__ ltab) {
   const double u = u_of_k(p, k);
-  return make_kterm_f(s, p, k, ltab, u, [&](double* cj, double* sj) { fm::sincos_(u * s.mu, sj, cj); });
+  return make_kterm_f(s, p, k, ltab, u, [&](double* cj, double* sj, double* ej) {
+    fm::sincos_(u * s.mu, sj, cj);
+    *ej = jump_gauss(s, u, ltab);
+  });
 }
 
 // strike-dependent constants of one option

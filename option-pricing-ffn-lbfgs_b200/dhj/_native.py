@@ -25,7 +25,7 @@ EXPORTS = (
     "dhj_market_create", "dhj_market_destroy", "dhj_loss_batch", "dhj_loss_fd", "dhj_market_prices",
     "dhj_cf", "dhj_truncation_range", "dhj_chi_psi", "dhj_fp64_peak",
     "dhj_lbfgs_create", "dhj_lbfgs_destroy", "dhj_lbfgs_ask", "dhj_lbfgs_tell", "dhj_lbfgs_result",
-    "dhj_generator_draws", "dhj_generate_dev", "dhj_generate",
+    "dhj_generator_draws", "dhj_generate_dev", "dhj_generate", "dhj_set_host_threads",
 )
 
 
@@ -99,6 +99,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
                     _c_i32, _F64, _c_i32, _c_f64, _c_i32, _c_f64]
         lib.dhj_generate_dev.argtypes = gen_head + [_c_vp] * 6
         lib.dhj_generate.argtypes = gen_head + [_c_vp] * 5
+        lib.dhj_set_host_threads.argtypes = [_c_i32]
         for name in EXPORTS:
             if name not in ("dhj_last_error",):
                 getattr(lib, name).restype = ctypes.c_int
@@ -476,6 +477,12 @@ def generator_draws(n, lo, hi, persistence, spot0, ret_mean, ret_sd, noise_sd, n
         raise NativeError(f"dhj_generator_draws failed ({rc})")
     np.random.set_state(("MT19937", key_out, pos_out.value, hg_out.value, cached_out.value))
     return params, spots, noise
+
+
+def set_host_threads(n: int) -> None:
+    """Threads of the library's host-side parallel loops (dhj_set_host_threads); 0 = all cores."""
+    if load_library().dhj_set_host_threads(int(n)) != 0:
+        raise NativeError("dhj_set_host_threads failed")
 
 
 def default_context() -> Context:

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Writes / updates one entry of profiles/ncu_summary.json from an .ncu-rep captured with `ncu --set full` on the
 CURRENT kernel sources (the entry records their sha; bench.py refuses the entry as stale when they change).
-usage: python scripts/ncu_to_summary.py <workload key: c2|c3|loss> <file.ncu-rep> <prices per launch> [note]"""
+usage: python scripts/ncu_to_summary.py <workload key: c2|c3|loss> <file.ncu-rep> <prices per launch> [note] [sha]
+(sha: kernel-source sha of the captured build if it is not the working tree, e.g. "round-1")"""
 import collections
 import csv
 import io
@@ -17,6 +18,7 @@ from bench import kernel_source_sha  # noqa: E402
 
 key, rep, n_prices = sys.argv[1], sys.argv[2], float(sys.argv[3])
 note = sys.argv[4] if len(sys.argv) > 4 else ""
+sha = sys.argv[5] if len(sys.argv) > 5 else kernel_source_sha()
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 val = dict(zip(rows[0], rows[2]))
@@ -48,7 +50,7 @@ time_unit = {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[unit["gpu__time_durati
 entry = {
     "kernel": val.get("Kernel Name", "?"),
     "capture": f"{rep} (ncu --set full --clock-control none); text summary beside it in profiles/",
-    "kernel_source_sha": kernel_source_sha(),
+    "kernel_source_sha": sha,
     "gpu_time_ms": num("gpu__time_duration.sum") * time_unit,
     "prices_per_launch": n_prices,
     "dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),

@@ -47,10 +47,10 @@ def bench(P, strikes, mats, N, reps):
     return ms, n / ms * 1e3
 
 
-if which in ("c2", "both"):
+if which in ("c2", "both", "all"):
     ms, pps = bench(1 << 20, np.array([90.0, 95, 100, 105, 110]), np.array([0.25, 0.5, 1.0]), 128, 5)
     print(f"[{tag}] C2 {ms:.2f} ms  {pps:.4g} prices/s")
-if which in ("c3", "both"):
+if which in ("c3", "both", "all"):
     ms, pps = bench(1024, np.linspace(80, 120, 200), np.linspace(0.25, 2.0, 20), 256, 5)
     print(f"[{tag}] C3 {ms:.2f} ms  {pps:.4g} prices/s")
 if which in ("loss", "all"):
