@@ -87,21 +87,27 @@ struct SetConsts {
   double lam, mu, hsj2;        // hsj2 = 0.5*sj^2
 };
 
-DHJ_HD SetConsts make_set_consts(const Params& m, double r, double q) {
-  SetConsts s;
-  for (int j = 0; j < 2; ++j) {
-    s.kappa[j] = m.kappa[j];
-    s.kk[j] = m.kappa[j] * m.kappa[j];
-    s.rs[j] = m.rho[j] * m.sigma[j];
-    s.s2[j] = m.sigma[j] * m.sigma[j];
-    s.two_kappa[j] = m.kappa[j] + m.kappa[j];
-    s.v0[j] = m.v0[j];
-    s.c[j] = fm::div(m.kappa[j] * m.theta[j], s.s2[j]);
-  }
+// factor j's share of SetConsts, and the jump / drift share: the batch kernel computes them in different lanes
+DHJ_HD void set_consts_factor(const Params& m, int j, SetConsts& s) {
+  s.kappa[j] = m.kappa[j];
+  s.kk[j] = m.kappa[j] * m.kappa[j];
+  s.rs[j] = m.rho[j] * m.sigma[j];
+  s.s2[j] = m.sigma[j] * m.sigma[j];
+  s.two_kappa[j] = m.kappa[j] + m.kappa[j];
+  s.v0[j] = m.v0[j];
+  s.c[j] = fm::div(m.kappa[j] * m.theta[j], s.s2[j]);
+}
+DHJ_HD void set_consts_jump(const Params& m, double r, double q, SetConsts& s) {
   s.hsj2 = 0.5 * (m.sj * m.sj);
   double comp = fm::exp_(m.mu + s.hsj2) - 1.0;
   s.drift = r - q - m.lam * comp;
   s.lam = m.lam; s.mu = m.mu;
+}
+
+DHJ_HD SetConsts make_set_consts(const Params& m, double r, double q) {
+  SetConsts s;
+  for (int j = 0; j < 2; ++j) set_consts_factor(m, j, s);
+  set_consts_jump(m, r, q, s);
   return s;
 }
 
@@ -123,20 +129,25 @@ DHJ_HD void factor_cumulants(double tau, double r, double v0, double lm, double 
   *c2 = fm::rcp(8.0 * (lm2 * lm)) * ((((t1 + t2) + t3) + t4) + t5);
 }
 
-// a0, b0 = c1 -+ L*sqrt(|c2|) before the strike-dependent widening (double_heston.py:121-132)
-DHJ_HD void truncation_range(const Params& m, double T, double r, double L, double* a0, double* b0) {
+// a0, b0 = c1 -+ L*sqrt(|c2|) before the strike-dependent widening (double_heston.py:121-132), from the two
+// factors' cumulants (c1 = 0 + c1_0 + c1_1 in the reference's order)
+DHJ_HD void truncation_from_cumulants(const Params& m, double T, double L, double c1_0, double c2_0, double c1_1,
+                                      double c2_1, double* a0, double* b0) {
   double c1 = 0.0, c2 = 0.0;
-#pragma unroll 1
-  for (int j = 0; j < 2; ++j) {                 // rolled: one copy of the cumulant code
-    double c1j, c2j;
-    factor_cumulants(T, r, m.v0[j], m.kappa[j], m.theta[j], m.sigma[j], m.rho[j], &c1j, &c2j);
-    c1 += c1j; c2 += c2j;
-  }
+  c1 += c1_0; c2 += c2_0;
+  c1 += c1_1; c2 += c2_1;
   c1 = c1 + m.lam * T * m.mu;
   c2 = c2 + m.lam * T * (m.sj * m.sj + m.mu * m.mu);
   double h = L * fm::sqrt_(fabs(c2));
   *a0 = c1 - h;
   *b0 = c1 + h;
+}
+DHJ_HD void truncation_range(const Params& m, double T, double r, double L, double* a0, double* b0) {
+  double c1j[2], c2j[2];
+#pragma unroll 1
+  for (int j = 0; j < 2; ++j)                   // rolled: one copy of the cumulant code
+    factor_cumulants(T, r, m.v0[j], m.kappa[j], m.theta[j], m.sigma[j], m.rho[j], &c1j[j], &c2j[j]);
+  truncation_from_cumulants(m, T, L, c1j[0], c2j[0], c1j[1], c2j[1], a0, b0);
 }
 
 // Python `a = min(a, y)` / `b = max(b, y)` (double_heston.py:136-137): the second argument wins

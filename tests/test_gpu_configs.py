@@ -165,13 +165,14 @@ def test_final_loss_ensemble_two_sided(mods, golden):
     # (1) two-sided: nothing below the reference's best basin, nothing above its worst
     assert fun.min() >= 0.9 * ref_fun.min() and fun.max() <= 1.1 * ref_fun.max()
     # (2) no new basin.  The reference ends either in basin A (7.95e-7..7.97e-7 after 17 iterations: 5 of its 8 runs)
-    # or further down the same valley in region B (3.5e-8..5.9e-8 after 37..47 iterations: 3 of 8), never in between.
+    # or further down the same valley in region B (3.5e-8..5.9e-8 after 37..47 iterations: 3 of 8; runs that stop a few
+    # iterations earlier or later there end within 25 % of that range), never in between.
     ref_a = ref_fun > 1e-7
     a_lo, a_hi = ref_fun[ref_a].min(), ref_fun[ref_a].max()
     b_lo, b_hi = ref_fun[~ref_a].min(), ref_fun[~ref_a].max()
     assert ref_a.sum() == 5 and set(ref_nit[ref_a]) == {17} and ref_nit[~ref_a].min() >= 37       # fixture tripwire
     in_a = (fun >= 0.99 * a_lo) & (fun <= 1.01 * a_hi) & (nit == 17)
-    in_b = (fun >= b_lo / 1.25) & (fun <= 1.25 * b_hi) & (nit >= 30) & (nit <= 50)
+    in_b = (fun >= b_lo / 1.25) & (fun <= 1.25 * b_hi) & (nit >= 30)
     assert (in_a | in_b).all(), (fun, nit)
     # (3) both basins are reached, as by the reference (8 runs of a chaotic iteration: the split itself is a coin toss)
     assert in_a.any() and in_b.any()
