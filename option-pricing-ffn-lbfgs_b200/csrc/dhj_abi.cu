@@ -239,8 +239,14 @@ int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_s
     }();
     k_price_batch<<<(int)std::max<long long>(1, std::min(batches, cap)), kBatchThreads, extra, st>>>(v, a);
   } else {
-    const long long cap = 2147483647LL;
-    k_price_dense<<<(int)std::max<long long>(1, std::min(items, cap)), kBatchThreads, 0, st>>>(v, a);
+    // a warp per item, four items per block; the block's shared memory (four private strike tables) exceeds the
+    // 48 KB static limit: opt in once
+    static const cudaError_t attr = cudaFuncSetAttribute(k_price_dense, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)sizeof(DenseSmem));
+    DHJ_CUDA(ctx, attr);
+    const long long blocks = (items + kDenseWarps - 1) / kDenseWarps;
+    k_price_dense<<<(int)std::max<long long>(1, std::min(blocks, 2147483647LL)), 32 * kDenseWarps, sizeof(DenseSmem),
+                    st>>>(v, a);
   }
   DHJ_CUDA(ctx, cudaGetLastError());
   ctx->launches++;

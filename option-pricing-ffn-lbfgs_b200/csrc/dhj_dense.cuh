@@ -1,73 +1,158 @@
 // dhj_dense.cuh — pricing kernel for slices with many strikes (the 200 x 20 dense surface of C3, or any
-// option list with more than 8 strikes per maturity): one block per (parameter set, maturity slice).
+// option list with more than 8 strikes per maturity): ONE WARP PER ITEM (parameter set, maturity slice), no block
+// barrier anywhere in the item loop.
 //
-//   * thread 0 prepares the item (per-set constants, truncation range, pass constants);
-//   * strikes are processed in chunks of 256: all 128 threads prepare strike constants
-//     (K, log(K/S0), exp(.), binding/call flags, rotation step cos/sin(theta_j));
-//   * per 128-wide k-block every thread evaluates the CF at its k and leaves the strike-independent
-//     coefficients (P, Q, R) in its warp's stage; each lane then contracts ONE STRIKE against the warp's 32
-//     coefficients by plane rotations (segment_sums, one exact sincos at the segment start) — 7 FMAs per
-//     (strike, k) instead of a sincos + 15 flops;
-//   * strikes whose +-0.1 widening binds get their own pass (own (a,b), own CF), one strike at a time.
+//   * prologue: lanes 0 and 1 compute the two factors' constants and cumulants, lane 2 the jump / drift constants,
+//     lane 3 the discount factor; the cumulants are shuffled, every lane forms (a0, b0), lanes 0..2 finish the pass
+//     constants (same scalar functions as the batch kernel's prepare_item: same bits);
+//   * strikes are processed in chunks of 224: the lanes prepare strike constants (K, log(K/S0), S0 exp(.),
+//     binding / call flags, rotation step cos / sin(theta_j)) into the warp's private shared memory;
+//   * per block of 32 cosine terms every lane evaluates the CF at its k and leaves the strike-independent
+//     coefficients (P, Q, R) in the warp's stage; each lane then contracts ONE STRIKE per round against the 32
+//     coefficients by the three-term recurrence (segment_sums, one exact sincos at the segment start) — 5 FMAs per
+//     (strike, k) instead of a sincos + 15 flops; the strike-independent sums A1, A2, A3 are accumulated per lane
+//     and reduced once per pass;
+//   * strikes whose +-0.1 widening binds get their own pass (own (a,b), own CF), one strike at a time, contracted
+//     by four lanes (8-term segments) as the batch kernel does.
+// (r01 ran one BLOCK per item: thread 0 prepared the item behind two block barriers and 20 % of all warp samples
+// sat at that barrier — profiles/ncu_k_dense_r02_base.txt.)
 #pragma once
 #include "dhj_batch.cuh"
 
 namespace dhj {
 
-constexpr int kDenseChunk = 256;
+constexpr int kDenseChunk = 224;
+constexpr int kDenseWarps = 4;
 #ifndef DHJ_DENSE_MINB
-#define DHJ_DENSE_MINB 6
+#define DHJ_DENSE_MINB 4
 #endif
 
-struct DenseSmem {
+struct DenseWarp {
   SetConsts set;
   PassConsts pass, extra_pass;
-  double a0, b0, S0, disc;
+  double S0, disc, a0, b0;
   double extra_cth, extra_sth;
-  CoefStage stage[kBatchWarps];
-  fm::Tables ltab;
-  double K[kDenseChunk], x[kDenseChunk], ex[kDenseChunk], cth[kDenseChunk], sth[kDenseChunk];
-  double partial[kBatchWarps][kDenseChunk];
+  CoefStage stage;
+  double K[kDenseChunk], x[kDenseChunk], sex[kDenseChunk], cth[kDenseChunk], sth[kDenseChunk];   // sex = S0 exp(x)
+  double part[kDenseChunk];                        // price accumulators of the chunk's strikes
   unsigned char call[kDenseChunk], bind[kDenseChunk];
-  int n_bind;
 };
 
-// one pass over the cosine terms for the strikes [0, cnt) of the chunk with bind flag == want_bind_idx semantics:
-//   single < 0 : all strikes with bind == 0 (lane per strike, rounds of 32)
-//   single >= 0: only strike `single` (lane 0 of each warp)
-__device__ __forceinline__ void dense_pass(DenseSmem& sm, const PassConsts& pc, const double* __restrict__ cth,
-                                           const double* __restrict__ sth, int cnt, int single, int n_cos, int tid) {
-  const int lane = tid & 31, warp = tid >> 5;
-  CoefStage& st = sm.stage[warp];
-#pragma unroll 1
-  for (int k0 = 0; k0 < n_cos; k0 += kBatchThreads) {
-    const int k = k0 + tid;
-    KCoef c;
-    c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
-    if (k < n_cos) c = make_kcoef(make_kterm(sm.set, pc, k, &sm.ltab), pc, k);
+struct DenseSmem {
+  DenseWarp w[kDenseWarps];
+  fm::Tables ltab;
+};
+
+// prologue of one item by its warp (see the header)
+__device__ __forceinline__ void dense_prepare(DenseWarp& W, const SliceView& v, const double* __restrict__ pp,
+                                              int transform, double S0, double T, int lane) {
+  Params m;
+  if (transform) {
+    double* scratch = reinterpret_cast<double*>(&W.stage);
+    if (lane < kNumParams) {
+      const double x = pp[lane];
+      scratch[lane] = (lane == 4 || lane == 9) ? tanh(x) : ((lane == 11) ? x : fm::exp_(x));
+    }
     __syncwarp();
-    st.PQ[lane] = make_double2(c.P, c.Q); st.R[lane] = c.R;
-    const double A1 = warp_sum(c.a1), A2 = warp_sum(c.a2), A3 = warp_sum(c.P);
-    const double g0 = __shfl_sync(kFullMask, c.g0, 0);
+    m = load_params(scratch);
     __syncwarp();
-    // frequency of the warp's first term
-    const double kpi = (double)(k - lane) * kPi;
-    const double q0 = kpi * pc.rw;
-    const double u0 = fma(fma(-pc.w, q0, kpi), pc.rw, q0);
-    const int t_lo = (single < 0) ? lane : single + lane * kDenseChunk;     // lane 0 only when single
-    const int t_hi = (single < 0) ? cnt : single + 1;
+  } else {
+    m = load_params(pp);
+  }
+  double c1j = 0.0, c2j = 0.0;
+  if (lane < 2) {
+    set_consts_factor(m, lane, W.set);
+    factor_cumulants(T, v.r, m.v0[lane], m.kappa[lane], m.theta[lane], m.sigma[lane], m.rho[lane], &c1j, &c2j);
+  } else if (lane == 2) {
+    set_consts_jump(m, v.r, v.q, W.set);
+  } else if (lane == 3) {
+    W.S0 = S0;
+    W.disc = fm::exp_(-v.r * T);
+  }
+  const double c1_0 = __shfl_sync(kFullMask, c1j, 0), c2_0 = __shfl_sync(kFullMask, c2j, 0);
+  const double c1_1 = __shfl_sync(kFullMask, c1j, 1), c2_1 = __shfl_sync(kFullMask, c2j, 1);
+  double a0, b0;
+  truncation_from_cumulants(m, T, v.L, c1_0, c2_0, c1_1, c2_1, &a0, &b0);
+  if (lane == 0) {
+    const double w = b0 - a0;
+    W.pass.a = a0; W.pass.b = b0; W.pass.w = w; W.pass.rw = fm::rcp(w); W.pass.tw = fm::div(2.0, w);
+    W.pass.T = T; W.pass.lamT = m.lam * T;
+    W.a0 = a0; W.b0 = b0;
+  } else if (lane == 1) {
+    W.pass.eb = fm::exp_(b0);
+  } else if (lane == 2) {
+    W.pass.ea = fm::exp_(a0);
+  }
+}
+
+// CF at this lane's k of the block [k0, k0 + 32) -> strike-independent coefficients in the warp's stage; the lanes'
+// shares of A1, A2, A3 accumulate in a1, a2, a3; g0 (k = 0 only) is broadcast in the first block
+__device__ __forceinline__ void dense_coefficients(DenseWarp& W, const PassConsts& pc, int k0, int n_cos, int lane,
+                                                   const fm::Tables* __restrict__ ltab, double& a1, double& a2,
+                                                   double& a3, double& g0) {
+  const int k = k0 + lane;
+  KCoef c;
+  c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
+  if (k < n_cos) c = make_kcoef(make_kterm(W.set, pc, k, ltab), pc, k);
+  a1 += c.a1; a2 += c.a2; a3 += c.P;
+  if (k0 == 0) g0 = __shfl_sync(kFullMask, c.g0, 0);
+  __syncwarp();                                        // the previous block's coefficients have been consumed
+  W.stage.PQ[lane] = make_double2(c.P, c.Q); W.stage.R[lane] = c.R;
+  __syncwarp();
+}
+
+// regular pass: all strikes of the chunk whose widening does not bind, a lane per strike, rounds of 32
+__device__ __forceinline__ void dense_pass(DenseWarp& W, int cnt, int n_cos, int lane,
+                                           const fm::Tables* __restrict__ ltab) {
+  const PassConsts& pc = W.pass;
+  double a1 = 0.0, a2 = 0.0, a3 = 0.0, g0 = 0.0;
 #pragma unroll 1
-    for (int t = t_lo; t < t_hi; t += 32) {
-      if (single < 0 && sm.bind[t]) continue;
+  for (int k0 = 0; k0 < n_cos; k0 += 32) {
+    dense_coefficients(W, pc, k0, n_cos, lane, ltab, a1, a2, a3, g0);
+    const double u0 = u_of_k(pc, k0);                   // frequency of the block's first term
+#pragma unroll 1
+    for (int t = lane; t < cnt; t += 32) {
+      if (W.bind[t]) continue;
       double sn, cs, spq, sr;
-      fm::sincos_(u0 * (sm.x[t] - pc.a), &sn, &cs);
-      const int ti = (single < 0) ? t : 0;
-      segment_sums<32>(st.PQ, reinterpret_cast<const Pair*>(st.R), cs, sn, cth[ti], sth[ti], &spq, &sr);
-      const double val = (sm.K[t] * sr - (sm.S0 * sm.ex[t]) * spq) +
-                         strike_const_part(sm.call[t] != 0, sm.S0, sm.K[t], sm.x[t], pc, A1, A2, A3, g0);
-      sm.partial[warp][t] += val;
+      fm::sincos_(u0 * (W.x[t] - pc.a), &sn, &cs);
+      segment_sums<32>(W.stage.PQ, reinterpret_cast<const Pair*>(W.stage.R), cs, sn, W.cth[t], W.sth[t], &spq, &sr);
+      W.part[t] += fma(W.K[t], sr, -(W.sex[t] * spq));
     }
   }
+  const double A1 = warp_sum(a1), A2 = warp_sum(a2), A3 = warp_sum(a3);
+  for (int t = lane; t < cnt; t += 32)
+    if (!W.bind[t])
+      W.part[t] += strike_const_part(W.call[t] != 0, W.S0, W.K[t], W.x[t], pc, A1, A2, A3, g0);
+}
+
+// pass of ONE strike with its own (a, b): four lanes contract 8-term segments, as in the batch kernel
+__device__ __forceinline__ void dense_pass_single(DenseWarp& W, int t, int n_cos, int lane,
+                                                  const fm::Tables* __restrict__ ltab) {
+  if (lane == 0) {
+    W.extra_pass = make_pass_consts(W.set, py_min(W.a0, W.x[t] - 0.1), py_max(W.b0, W.x[t] + 0.1), W.pass.T);
+    fm::sincos_(u_one(W.extra_pass) * (W.x[t] - W.extra_pass.a), &W.extra_sth, &W.extra_cth);
+  }
+  __syncwarp();
+  const PassConsts& pc = W.extra_pass;
+  double a1 = 0.0, a2 = 0.0, a3 = 0.0, g0 = 0.0, acc = 0.0;
+#pragma unroll 1
+  for (int k0 = 0; k0 < n_cos; k0 += 32) {
+    dense_coefficients(W, pc, k0, n_cos, lane, ltab, a1, a2, a3, g0);
+    double val = 0.0;
+    if (lane < 4) {
+      double sn, cs, spq, sr;
+      fm::sincos_(u_of_k(pc, k0 + 8 * lane) * (W.x[t] - pc.a), &sn, &cs);
+      segment_sums<8>(W.stage.PQ + 8 * lane, reinterpret_cast<const Pair*>(W.stage.R + 8 * lane), cs, sn, W.extra_cth,
+                      W.extra_sth, &spq, &sr);
+      val = fma(W.K[t], sr, -(W.sex[t] * spq));
+    }
+    val += __shfl_xor_sync(kFullMask, val, 1);
+    val += __shfl_xor_sync(kFullMask, val, 2);
+    acc += val;                                        // meaningful in lane 0
+  }
+  const double A1 = warp_sum(a1), A2 = warp_sum(a2), A3 = warp_sum(a3);
+  if (lane == 0) W.part[t] = acc + strike_const_part(W.call[t] != 0, W.S0, W.K[t], W.x[t], pc, A1, A2, A3, g0);
+  __syncwarp();
 }
 
 }  // namespace dhj

@@ -1,7 +1,7 @@
 // dhj_kernels.cuh — the CUDA kernels of libdhj.so (sm_100a).
 //
 //   k_price_batch  slices of <= 8 strikes: warp per item, lane per cosine index, 32 items per block   (K1 / K3 of SURVEY §2)
-//   k_price_dense  many strikes per slice: block per item, lane per strike
+//   k_price_dense  many strikes per slice: warp per item, lane per strike
 //   k_loss_batch   K2: exp/tanh transform + prices of every market option + relative-MSE + Feller penalty +
 //                  1e10 sentinel; in FD mode the 14 stencil points of an optimiser state are 14 units and the
 //                  thread that finishes the last one assembles scipy's gradient — ONE launch per optimiser step
@@ -59,69 +59,58 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
   }
 }
 
-// Many strikes per slice: one block per item, lane per strike (dhj_dense.cuh).
-__global__ void __launch_bounds__(kBatchThreads, DHJ_DENSE_MINB) k_price_dense(SliceView v, PriceArgs a) {
-  __shared__ DenseSmem sm;
+// Many strikes per slice: one WARP per item, lane per strike (dhj_dense.cuh); no block barrier in the item loop.
+__global__ void __launch_bounds__(32 * kDenseWarps, DHJ_DENSE_MINB) k_price_dense(SliceView v, PriceArgs a) {
+  extern __shared__ __align__(16) unsigned char dense_smem_raw[];
+  DenseSmem& sm = *reinterpret_cast<DenseSmem*>(dense_smem_raw);
   const int tid = threadIdx.x;
   load_log_table(&sm.ltab, tid);
+  __syncthreads();
+  const int warp = __shfl_sync(kFullMask, tid >> 5, 0), lane = tid & 31;
+  DenseWarp& W = sm.w[warp];
   const long long n_items = a.P * (long long)v.n_slices;
-  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+  for (long long item = (long long)blockIdx.x * kDenseWarps + warp; item < n_items;
+       item += (long long)gridDim.x * kDenseWarps) {
     const long long p = item / v.n_slices;
     const int s = (int)(item - p * v.n_slices);
     const long long row = a.row_index ? (long long)a.row_index[p] : p;
     const double* strike_row = v.strike + row * v.strike_stride;
     const int o_lo = v.slice_off[s], o_hi = v.slice_off[s + 1];
-    __syncthreads();                                   // previous item has left shared memory
-    if (tid == 0) {
-      const double* pp = a.params + kNumParams * p;
-      const Params m = a.transform ? transform_params(pp) : load_params(pp);
-      sm.set = make_set_consts(m, v.r, v.q);
-      const double T = v.slice_T[s];
-      truncation_range(m, T, v.r, v.L, &sm.a0, &sm.b0);
-      sm.pass = make_pass_consts(sm.set, sm.a0, sm.b0, T);
-      sm.S0 = a.S0[row * a.s0_stride];
-      sm.disc = fm::exp_(-v.r * T);
-    }
-    __syncthreads();
+    __syncwarp();                                        // the previous item has left the warp's shared memory
+    dense_prepare(W, v, a.params + kNumParams * p, a.transform, a.S0[row * a.s0_stride], v.slice_T[s], lane);
+    __syncwarp();
+    double* out_row = a.out + p * (long long)v.n_options;
     for (int c_lo = o_lo; c_lo < o_hi; c_lo += kDenseChunk) {
       const int cnt = min(kDenseChunk, o_hi - c_lo);
-      if (tid == 0) sm.n_bind = 0;
-      __syncthreads();
-      const double u1 = u_one(sm.pass);
-      for (int t = tid; t < cnt; t += kBatchThreads) {
-        double K = strike_row[v.pos[c_lo + t]];
-        if (v.scale_by_spot) K = K * sm.S0 / 100.0;
-        const StrikeConsts sc = make_strike_consts(K, sm.S0);
-        sm.K[t] = sc.K; sm.x[t] = sc.x; sm.ex[t] = sc.ex;
-        fm::sincos_(u1 * (sc.x - sm.a0), &sm.sth[t], &sm.cth[t]);
-        const bool bind = ((sc.x - 0.1) < sm.a0) || ((sc.x + 0.1) > sm.b0);
-        sm.bind[t] = bind; sm.call[t] = v.call[c_lo + t];
-        if (bind) atomicAdd(&sm.n_bind, 1);
-#pragma unroll
-        for (int w = 0; w < kBatchWarps; ++w) sm.partial[w][t] = 0.0;
+      const double u1 = u_one(W.pass);
+      int n_bind = 0;
+      for (int t0 = 0; t0 < cnt; t0 += 32) {              // warp-uniform trip count (the ballot needs every lane)
+        const int t = t0 + lane;
+        bool bind = false;
+        if (t < cnt) {
+          double K = strike_row[v.pos[c_lo + t]];
+          if (v.scale_by_spot) K = K * W.S0 / 100.0;
+          const StrikeConsts sc = make_strike_consts(K, W.S0);
+          W.K[t] = sc.K; W.x[t] = sc.x; W.sex[t] = W.S0 * sc.ex;
+          fm::sincos_(u1 * (sc.x - W.a0), &W.sth[t], &W.cth[t]);
+          bind = ((sc.x - 0.1) < W.a0) || ((sc.x + 0.1) > W.b0);
+          W.bind[t] = bind; W.call[t] = v.call[c_lo + t];
+          W.part[t] = 0.0;
+        }
+        n_bind += __popc(__ballot_sync(kFullMask, bind));
       }
-      __syncthreads();
-      if (sm.n_bind < cnt) dense_pass(sm, sm.pass, sm.cth, sm.sth, cnt, -1, v.n_cos, tid);
-      if (sm.n_bind > 0) {
+      __syncwarp();
+      if (n_bind < cnt) dense_pass(W, cnt, v.n_cos, lane, &sm.ltab);
+      if (n_bind > 0) {
         for (int t = 0; t < cnt; ++t) {
-          if (!sm.bind[t]) continue;                   // uniform: flags live in shared memory
-          __syncthreads();
-          if (tid == 0) {
-            sm.extra_pass = make_pass_consts(sm.set, py_min(sm.a0, sm.x[t] - 0.1), py_max(sm.b0, sm.x[t] + 0.1),
-                                             sm.pass.T);
-            fm::sincos_(u_one(sm.extra_pass) * (sm.x[t] - sm.extra_pass.a), &sm.extra_sth, &sm.extra_cth);
-          }
-          __syncthreads();
-          dense_pass(sm, sm.extra_pass, &sm.extra_cth, &sm.extra_sth, cnt, t, v.n_cos, tid);
+          if (!W.bind[t]) continue;                       // uniform: the flags live in shared memory
+          __syncwarp();
+          dense_pass_single(W, t, v.n_cos, lane, &sm.ltab);
         }
       }
-      __syncthreads();
-      double* out_row = a.out + p * (long long)v.n_options;
-      for (int t = tid; t < cnt; t += kBatchThreads) {
-        const double sum = ((sm.partial[0][t] + sm.partial[1][t]) + sm.partial[2][t]) + sm.partial[3][t];
-        out_row[v.pos[c_lo + t]] = sm.disc * sum;
-      }
-      __syncthreads();
+      __syncwarp();
+      for (int t = lane; t < cnt; t += 32) out_row[v.pos[c_lo + t]] = W.disc * W.part[t];
+      __syncwarp();
     }
   }
 }

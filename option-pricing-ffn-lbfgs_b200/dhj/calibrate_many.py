@@ -85,8 +85,19 @@ _PIPELINE_MIN_MARKETS = 2048        # below this one lock-step loop is launch-la
 _pipeline_contexts: list = []       # second context (own stream and staging) for the second pipeline, made once
 
 
+def default_pipelines() -> int:
+    """Host pipelines for large batches: enough to keep the GPU busy while other pipelines' host optimisers work
+    (measured on one B200, 10 000 markets x 3 starts: 1 pipeline 0.79 s, 2: 0.74, 3: 0.60, 6: 0.56), bounded by
+    the cores this process may use (a rank of a multi-GPU job is bound to its share of the host)."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    return max(1, min(6, cores // 2))
+
+
 def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, maxiter=300, multi_start=3,
-                   x0=None, ctx: Context | None = None, return_all_starts=False, pipelines=2):
+                   x0=None, ctx: Context | None = None, return_all_starts=False, pipelines=None):
     """Calibrate n markets simultaneously.
 
     spots[n]; strikes[M] or [n, M]; maturities[M]; is_call[M]; prices[n, M]; optional x0[n, multi_start, 13].
@@ -94,13 +105,15 @@ def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, 
     best_start[n], model_prices[n,M], rounds (launches), seconds; with `return_all_starts` also the per-start
     x / loss / nit / status.
 
-    With `pipelines=k` (default 2) and enough markets the set is cut in k parts that run their lock-step loops in k
+    With `pipelines=k` (default: `default_pipelines()`) and enough markets the set is cut in k parts that run their lock-step loops in k
     threads on k contexts (streams) of the same GPU: while one half's loss launch runs, the other half's host
     optimiser (ask / tell, C++ under a released GIL) works — part of the host share of a round (~20 %) disappears
     from the wall time (10 000 markets: 0.80 -> 0.73 s).  Every optimiser state is independent of the others, so the result does not depend on the split.
     """
     t0 = time.time()
     n_all = np.asarray(spots).size
+    if pipelines is None:
+        pipelines = default_pipelines()
     if pipelines > 1 and ctx is None and n_all >= _PIPELINE_MIN_MARKETS:
         return _calibrate_pipelined(spots, risk_free_rate, strikes, maturities, is_call, prices, maxiter, multi_start,
                                     x0, return_all_starts, t0, int(pipelines))
