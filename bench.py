@@ -355,7 +355,7 @@ class ClockSampler:
 def bind_rank_to_cores(local: int, world: int):
     """With several ranks on one host, give each rank its own slice of the cores NVML names as near its GPU (before
     any pinned allocation: first touch decides the memory node).  Returns a description for the JSON line."""
-    if world <= 1:
+    if world <= 1 or os.environ.get("BENCH_NO_BIND"):
         return None
     try:
         import pynvml

@@ -124,6 +124,10 @@ DHJ_API int dhj_market_prices(dhj_ctx* ctx, const dhj_market* market, const doub
 /* characteristic_function(phi, tau) at n real frequencies u[n] (double_heston.py:48-97). */
 DHJ_API int dhj_cf(dhj_ctx* ctx, const double* params, double r, double q, double tau, const double* u, int32_t n,
            double* out_re, double* out_im);
+/* Same for COMPLEX frequencies u = u_re + i u_im (the reference's method accepts them; the pricing path does not use
+ * them): the reference's own operation order in complex arithmetic. */
+DHJ_API int dhj_cf_complex(dhj_ctx* ctx, const double* params, double r, double q, double tau, const double* u_re,
+                           const double* u_im, int32_t n, double* out_re, double* out_im);
 /* truncationRange(L): (a,b) for P sets x M options, out_ab[P][M][2] (double_heston.py:100-139). */
 DHJ_API int dhj_truncation_range(dhj_ctx* ctx, const double* params, int64_t P, const double* S0, int64_t s0_stride,
                          double r, const double* strike, const double* maturity, int32_t M, double L,

@@ -128,7 +128,11 @@ struct BookSlot {
   cudaStream_t upload_stream = nullptr;
 };
 
-constexpr int kSlots = 2;
+// Chunks of a host-buffer call rotate through three slots (stream + device buffers + pinned staging each): a slot's
+// upload, kernel and download are serialised by its stream, so with two slots a chunk every (H2D + kernel + D2H) / 2
+// is the best the pipeline can do — slower than the kernel as soon as the host link gives a rank less than ~20 GB/s
+// (eight ranks copying at once on one host: 11.5 GB/s down per GPU, measured; profiles/README.md r02).
+constexpr int kSlots = 3;
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
@@ -355,7 +359,7 @@ int run_price_host(dhj_ctx* ctx, SliceView v, int max_slice, const double* param
   const long fail_at = fail_env ? atol(fail_env) : -1;
   int slot_i = 0;
   int64_t lo = 0;
-  for (size_t ci = 0; ci < sizes.size(); lo += sizes[ci], ++ci, slot_i ^= 1) {
+  for (size_t ci = 0; ci < sizes.size(); lo += sizes[ci], ++ci, slot_i = (slot_i + 1) % kSlots) {
     const int64_t n = sizes[ci];
     Slot& sl = ctx->slots[slot_i];
     if ((long)ci == fail_at) return fail(ctx, DHJ_ERR_NOMEM, "injected failure at chunk %ld (DHJ_DEBUG_FAIL_AT_CHUNK)", fail_at);
@@ -835,6 +839,29 @@ int dhj_cf(dhj_ctx* ctx, const double* params, double r, double q, double tau, c
   return DHJ_OK;
 }
 
+int dhj_cf_complex(dhj_ctx* ctx, const double* params, double r, double q, double tau, const double* u_re,
+                   const double* u_im, int32_t n, double* out_re, double* out_im) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  if (!params || !u_re || !u_im || !out_re || !out_im || n < 0) return fail(ctx, DHJ_ERR_ARG, "bad arguments");
+  if (n == 0) return DHJ_OK;
+  Staged st{ctx};
+  const size_t pb = kNumParams * sizeof(double), ub = (size_t)n * sizeof(double);
+  int rc = st.begin(pb + 2 * ub, 2 * ub);
+  if (rc) return rc;
+  memcpy(st.hin(), params, pb);
+  memcpy(st.hin() + pb, u_re, ub);
+  memcpy(st.hin() + pb + ub, u_im, ub);
+  if ((rc = st.upload())) return rc;
+  double* dout = (double*)ctx->d_prices.p;
+  k_cf_complex<<<(n + 127) / 128, 128, 0, ctx->stream>>>((const double*)st.din(), r, q, tau,
+                                                          (const double*)(st.din() + pb),
+                                                          (const double*)(st.din() + pb + ub), n, dout, dout + n);
+  if ((rc = st.download())) return rc;
+  memcpy(out_re, ctx->h_res.p, ub);
+  memcpy(out_im, (unsigned char*)ctx->h_res.p + ub, ub);
+  return DHJ_OK;
+}
+
 int dhj_truncation_range(dhj_ctx* ctx, const double* params, int64_t P, const double* S0, int64_t s0_stride,
                          double r, const double* strike, const double* maturity, int32_t M, double L,
                          double* out_ab) {
@@ -995,7 +1022,7 @@ int dhj_generate(dhj_ctx* ctx, uint64_t seed, int64_t first, int64_t n, int32_t 
     sl.pending = false; sl.user_out = nullptr; sl.out_bytes = 0; sl.pieces.clear();
   }
   int slot_i = 0;
-  for (int64_t lo_i = 0; lo_i < n; lo_i += chunk, slot_i ^= 1) {
+  for (int64_t lo_i = 0; lo_i < n; lo_i += chunk, slot_i = (slot_i + 1) % kSlots) {
     const int64_t cnt = std::min(chunk, n - lo_i);
     Slot& sl = ctx->slots[slot_i];
     DHJ_CUDA(ctx, cudaEventSynchronize(sl.done));

@@ -7,7 +7,7 @@
 //                  thread that finishes the last one assembles scipy's gradient — ONE launch per optimiser step
 //   k_fd_expand / k_loss_reduce  K2 around the pricing kernels: markets with > 8 strikes per maturity, and any
 //                  batch of >= 8 192 loss evaluations (full 32-item batches balance the warps better)
-//   k_cf / k_truncation_range / k_chi_psi  the remaining public methods of DoubleHeston
+//   k_cf / k_cf_complex / k_truncation_range / k_chi_psi  the remaining public methods of DoubleHeston
 //   k_fp64_peak    DFMA-chain probe for the FP64 roofline denominator
 #pragma once
 #include "dhj_engine.cuh"
@@ -277,6 +277,70 @@ __global__ void k_cf(const double* __restrict__ params, double r, double q, doub
   const double mag = fm::exp_(xr);
   out_re[i] = mag * cs;
   out_im[i] = mag * sn;
+}
+
+// characteristic_function(phi, tau) for COMPLEX phi (the reference's ufunc arithmetic accepts it, double_heston.py:48-97;
+// nothing on the pricing path needs it).  Plain complex arithmetic in the reference's own operation order — Smith's
+// division as NumPy does it, glibc-style csqrt, libdevice exp / log / sincos / atan2 — one thread per frequency.
+struct Cx { double re, im; };
+__device__ __forceinline__ Cx cx_add(Cx a, Cx b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ Cx cx_sub(Cx a, Cx b) { return {a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ Cx cx_mul(Cx a, Cx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ Cx cx_scale(Cx a, double f) { return {a.re * f, a.im * f}; }
+__device__ __forceinline__ Cx cx_div(Cx a, Cx b) {
+  if (fabs(b.re) >= fabs(b.im)) {
+    const double rat = b.im / b.re, scl = 1.0 / (b.re + b.im * rat);
+    return {(a.re + a.im * rat) * scl, (a.im - a.re * rat) * scl};
+  }
+  const double rat = b.re / b.im, scl = 1.0 / (b.re * rat + b.im);
+  return {(a.re * rat + a.im) * scl, (a.im * rat - a.re) * scl};
+}
+__device__ __forceinline__ Cx cx_sqrt(Cx z) {
+  const double h = hypot(z.re, z.im);
+  if (h == 0.0) return {0.0, z.im};
+  if (z.re > 0.0) { const double t = sqrt(0.5 * (h + z.re)); return {t, 0.5 * (z.im / t)}; }
+  const double t = sqrt(0.5 * (h - z.re));
+  return {fabs(0.5 * (z.im / t)), copysign(t, z.im)};
+}
+__device__ __forceinline__ Cx cx_exp(Cx z) {
+  double sn, cs;
+  sincos(z.im, &sn, &cs);
+  const double e = exp(z.re);
+  return {e * cs, e * sn};
+}
+__device__ __forceinline__ Cx cx_log(Cx z) { return {log(hypot(z.re, z.im)), atan2(z.im, z.re)}; }
+
+__global__ void k_cf_complex(const double* __restrict__ params, double r, double q, double tau,
+                             const double* __restrict__ u_re, const double* __restrict__ u_im, int n,
+                             double* __restrict__ out_re, double* __restrict__ out_im) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Params m = load_params(params);
+  const Cx u = {u_re[i], u_im[i]};
+  const Cx iu = {-u.im, u.re};                                           // i u
+  const Cx one = {1.0, 0.0};
+  const double comp = exp(m.mu + 0.5 * m.sj * m.sj) - 1.0;               // :82
+  Cx A = cx_scale(iu, (r - q - m.lam * comp) * tau);                     // :83
+  Cx BV = {0.0, 0.0};
+  const Cx uu = cx_mul(u, Cx{u.re, u.im + 1.0});                         // u (u + i)
+  for (int j = 0; j < 2; ++j) {
+    const double s2 = m.sigma[j] * m.sigma[j];
+    const Cx beta = {m.kappa[j] - m.rho[j] * m.sigma[j] * iu.re, -(m.rho[j] * m.sigma[j]) * iu.im};   // :64, :73
+    const Cx d = cx_sqrt(cx_add(cx_mul(beta, beta), cx_scale(uu, s2)));                                 // :65, :74
+    const Cx bm = cx_sub(beta, d);
+    const Cx g = cx_div(bm, cx_add(beta, d));                                                           // :67, :76
+    const Cx E = cx_exp(cx_scale(d, -tau));
+    const Cx one_gE = cx_sub(one, cx_mul(g, E));
+    const Cx B = cx_mul(cx_scale(bm, 1.0 / s2), cx_div(cx_sub(one, E), one_gE));                        // :70-71, :79-80
+    const Cx lg = cx_log(cx_div(one_gE, cx_sub(one, g)));
+    A = cx_add(A, cx_scale(cx_sub(cx_scale(bm, tau), cx_scale(lg, 2.0)), m.kappa[j] * m.theta[j] / s2));   // :85-91
+    BV = cx_add(BV, cx_scale(B, m.v0[j]));
+  }
+  const Cx je = cx_exp(cx_sub(cx_scale(iu, m.mu), cx_scale(cx_mul(u, u), 0.5 * m.sj * m.sj)));
+  const Cx cf_jump = cx_exp(cx_scale(cx_sub(je, one), m.lam * tau));                                    // :93
+  const Cx cf = cx_mul(cx_exp(cx_add(A, BV)), cf_jump);                                                  // :94-96
+  out_re[i] = cf.re;
+  out_im[i] = cf.im;
 }
 
 // truncationRange(L) for P parameter sets x M (S0, K, T) triples (double_heston.py:100-139)

@@ -23,7 +23,7 @@ EXPORTS = (
     "dhj_abi_version", "dhj_device_count", "dhj_init", "dhj_destroy", "dhj_last_error", "dhj_launch_count",
     "dhj_price_list", "dhj_price_grid", "dhj_price_grid_dev",
     "dhj_market_create", "dhj_market_destroy", "dhj_loss_batch", "dhj_loss_fd", "dhj_market_prices",
-    "dhj_cf", "dhj_truncation_range", "dhj_chi_psi", "dhj_fp64_peak",
+    "dhj_cf", "dhj_cf_complex", "dhj_truncation_range", "dhj_chi_psi", "dhj_fp64_peak",
     "dhj_lbfgs_create", "dhj_lbfgs_destroy", "dhj_lbfgs_ask", "dhj_lbfgs_tell", "dhj_lbfgs_result",
     "dhj_generator_draws", "dhj_generate_dev", "dhj_generate", "dhj_set_host_threads",
 )
@@ -79,6 +79,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.dhj_loss_fd.argtypes = [_c_vp, _c_vp, _F64, _c_vp, _c_i64, _c_f64, _F64, _F64, _c_vp]
         lib.dhj_market_prices.argtypes = [_c_vp, _c_vp, _F64, _c_vp, _c_i64, _F64]
         lib.dhj_cf.argtypes = [_c_vp, _F64, _c_f64, _c_f64, _c_f64, _F64, _c_i32, _F64, _F64]
+        lib.dhj_cf_complex.argtypes = [_c_vp, _F64, _c_f64, _c_f64, _c_f64, _F64, _F64, _c_i32, _F64, _F64]
         lib.dhj_truncation_range.argtypes = [_c_vp, _F64, _c_i64, _F64, _c_i64, _c_f64, _F64, _F64, _c_i32, _c_f64,
                                              _F64]
         lib.dhj_chi_psi.argtypes = [_c_vp, _I32, _c_i32, _c_f64, _c_f64, _c_f64, _c_f64, _F64, _F64]
@@ -261,6 +262,16 @@ class Context:
 
     # -- the remaining DoubleHeston methods -------------------------------------------------------
     def cf(self, params, r, q, tau, u) -> np.ndarray:
+        """characteristic_function at real (dhj_cf) or complex (dhj_cf_complex) frequencies `u`."""
+        u = np.asarray(u)
+        if np.iscomplexobj(u):
+            flat = np.ascontiguousarray(u, dtype=np.complex128).reshape(-1)
+            ur, ui = np.ascontiguousarray(flat.real), np.ascontiguousarray(flat.imag)
+            re, im = np.empty_like(ur), np.empty_like(ur)
+            with self._lock:
+                self._check(self._lib.dhj_cf_complex(self._h, _f64(params, (N_PARAMS,)), float(r), float(q),
+                                                     float(tau), ur, ui, ur.size, re, im), "dhj_cf_complex")
+            return (re + 1j * im).reshape(u.shape)
         u = _f64(u)
         flat = u.reshape(-1)
         re, im = np.empty_like(flat), np.empty_like(flat)

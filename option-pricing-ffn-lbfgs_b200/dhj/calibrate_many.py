@@ -81,19 +81,20 @@ def initial_guesses(spots, strikes, maturities, prices, multi_start=3) -> np.nda
     return inverse_transform(p)
 
 
-_PIPELINE_MIN_MARKETS = 2048        # below this one lock-step loop is launch-latency bound anyway
+_PIPELINE_MIN_MARKETS = 512         # below this the per-pipeline setup costs more than the overlap returns
 _pipeline_contexts: list = []       # second context (own stream and staging) for the second pipeline, made once
 
 
 def default_pipelines() -> int:
     """Host pipelines for large batches: enough to keep the GPU busy while other pipelines' host optimisers work
-    (measured on one B200, 10 000 markets x 3 starts: 1 pipeline 0.79 s, 2: 0.74, 3: 0.60, 6: 0.56), bounded by
+    (measured on one B200, 10 000 markets x 3 starts: 1 pipeline 0.76 s, 2: 0.68, 4: 0.55, 6: 0.55; 1 250 markets:
+    0.146 / 0.132 / 0.111 / 0.126 s), bounded by
     the cores this process may use (a rank of a multi-GPU job is bound to its share of the host)."""
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    return max(1, min(6, cores // 2))
+    return max(1, min(4, cores // 2))
 
 
 def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, maxiter=300, multi_start=3,
@@ -131,6 +132,8 @@ def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, 
     rounds, active_sum = 0, 0
     t_ask = t_loss = t_tell = 0.0
     clock = time.perf_counter
+    t_loop0 = clock()
+    t_setup = time.time() - t0
     while True:
         ta = clock()
         idx, x = opt.ask()
@@ -145,6 +148,7 @@ def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, 
         t_tell += clock() - tc
         rounds += 1
         active_sum += idx.size
+    t_loop1 = clock()
     xs, fs, nit, nfev, status = opt.result()
     opt.close()
     fs2, xs2 = fs.reshape(n, multi_start), xs.reshape(n, multi_start, 13)
@@ -164,6 +168,7 @@ def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, 
         'seconds': time.time() - t0,
         # where the wall time of the lock-step loop went: device launches incl. copies / host optimiser
         'seconds_loss': t_loss, 'seconds_ask': t_ask, 'seconds_tell': t_tell, 'state_rounds': active_sum,
+        'seconds_setup': t_setup, 'seconds_loop': t_loop1 - t_loop0,
     }
     if return_all_starts:
         out.update({'all_x': xs2, 'all_loss': fs2, 'all_nit': nit.reshape(n, multi_start),
@@ -219,7 +224,7 @@ def _calibrate_pipelined(spots, risk_free_rate, strikes, maturities, is_call, pr
         if isinstance(val, np.ndarray):
             out[key] = np.concatenate([part[key] for part in parts], axis=0)
     out['rounds'] = max(part['rounds'] for part in parts)
-    for key in ('seconds_loss', 'seconds_ask', 'seconds_tell', 'state_rounds'):      # per pipeline (they overlap)
+    for key in ('seconds_loss', 'seconds_ask', 'seconds_tell', 'state_rounds', 'seconds_setup', 'seconds_loop'):
         out[key] = [part[key] for part in parts]
     out['launches'] = sum(part['rounds'] for part in parts)
     out['evaluations'] = sum(part['evaluations'] for part in parts)

@@ -64,8 +64,10 @@ class DoubleHeston():
 
     # -- reference API ----------------------------------------------------------------------------
     def characteristic_function(self, phi, tau):
-        """phi(u; tau) of the log-return (double_heston.py:48-97); scalar or array `phi`."""
-        cf = self._ctx.cf(self._params(), self.r, self.q, tau, np.asarray(phi, dtype=np.float64))
+        """phi(u; tau) of the log-return (double_heston.py:48-97); scalar or array `phi`, real or complex."""
+        arr = np.asarray(phi)
+        arr = arr.astype(np.complex128) if np.iscomplexobj(arr) else arr.astype(np.float64)
+        cf = self._ctx.cf(self._params(), self.r, self.q, tau, arr)
         return cf if np.ndim(phi) else np.complex128(cf)
 
     def truncationRange(self, L=10):

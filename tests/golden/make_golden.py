@@ -17,6 +17,7 @@ Fixtures (all float64, written with numpy.savez so values round-trip bit-exactly
                        (short maturities / far strikes) where the +-0.1 widening binds
   edge_cases.npz       Appendix-B style single prices (puts, q, degenerate parameters, N sweep)
   cf_values.npz        characteristic_function(u, tau) samples (double_heston.py:48-97)
+  cf_complex.npz       the same at complex phi
   loss_cases.npz       compute_loss at 64 x vectors incl. Feller-active and sentinel cases, and
                        the 14-evaluation forward-difference stencil scipy uses (lbfgs_calibrator.py:118-177)
   initial_guess.npz    get_initial_guess(0/1/2) under np.random.seed(0) (lbfgs_calibrator.py:179-234)
@@ -199,6 +200,22 @@ def make_cf_values():
             for j, u in enumerate(us):
                 cf[p, i, j] = dh.characteristic_function(float(u), float(tau))
     save("cf_values.npz", params=params, taus=taus, us=us, r=r, q=q, cf=cf)
+
+
+def make_cf_complex():
+    """characteristic_function at COMPLEX phi (the reference's arithmetic is complex throughout and accepts it)."""
+    rng = np.random.default_rng(20260106)
+    params = np.vstack([TEST_SUITE_PARAMS, DEMO_PARAMS, rng.uniform(GEN_RANGES[:, 0], GEN_RANGES[:, 1], size=(2, 13))])
+    taus = np.array([0.25, 1.0])
+    us = np.concatenate([[0.0 - 1.0j, 0.5 - 0.5j, 1e-8 + 0.0j], rng.uniform(0, 40, 17) + 1j * rng.uniform(-1.0, 0.5, 17)])
+    r, q = 0.03, 0.01
+    cf = np.zeros((len(params), len(taus), len(us)), dtype=np.complex128)
+    for p in range(len(params)):
+        dh = DoubleHeston(100, 100, 1.0, r, *[float(v) for v in params[p]], option_type="C", q=q)
+        for i, tau in enumerate(taus):
+            for j, u in enumerate(us):
+                cf[p, i, j] = dh.characteristic_function(complex(u), float(tau))
+    save("cf_complex.npz", params=params, taus=taus, us=us, r=r, q=q, cf=cf)
 
 
 def c1_market():
@@ -414,6 +431,7 @@ MAKERS = {
     "dense_surface": make_dense_surface,
     "edge_cases": make_edge_cases,
     "cf_values": make_cf_values,
+    "cf_complex": make_cf_complex,
     "loss_cases": make_loss_cases,
     "initial_guess": make_initial_guess,
     "generator": make_generator,

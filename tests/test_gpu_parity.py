@@ -110,6 +110,24 @@ def test_cf_golden(ctx, golden):
             assert (np.abs(got - want) <= 2e-13 * np.abs(want) + 1e-300).all(), (p, i)
 
 
+def test_cf_complex_golden(ctx, golden):
+    """characteristic_function at COMPLEX phi (dhj_cf_complex) against the reference's own values."""
+    g = golden("cf_complex.npz")
+    worst = 0.0
+    for p in range(g["params"].shape[0]):
+        for i, tau in enumerate(g["taus"]):
+            got = ctx.cf(g["params"][p], float(g["r"]), float(g["q"]), float(tau), g["us"])
+            want = g["cf"][p, i]
+            worst = max(worst, (np.abs(got - want) / np.maximum(np.abs(want), 1e-300)).max())
+    print("complex-phi CF: max rel err %.3e" % worst)
+    assert worst <= 1e-12
+    # real frequencies through the complex entry point agree with the real one
+    u = np.linspace(0.5, 60.0, 9)
+    a = ctx.cf(g["params"][0], 0.03, 0.0, 0.5, u)
+    b = ctx.cf(g["params"][0], 0.03, 0.0, 0.5, u.astype(np.complex128))
+    assert np.abs(a - b).max() <= 2e-13 * np.abs(a).max()
+
+
 def test_chi_psi(ctx):
     # double_heston.py:141-158 against the scalar oracle
     a, b, x = -2.8282625135277004, 2.9482625135277005, np.log(95.0 / 100.0)

@@ -111,6 +111,15 @@ def test_oracle_cf(golden):
     assert np.all(g["cf"][:, :, 0] == 1.0)          # phi(0) = 1 exactly
 
 
+def test_oracle_cf_complex(golden):
+    """characteristic_function at complex phi: the vectorised oracle against the reference's values."""
+    g = golden("cf_complex.npz")
+    for p in range(g["params"].shape[0]):
+        for i, tau in enumerate(g["taus"]):
+            vec = O.cf_vec(g["us"], float(tau), g["params"][p], float(g["r"]), float(g["q"]))
+            assert np.abs(vec - g["cf"][p, i]).max() <= 2e-13 * np.maximum(1.0, np.abs(g["cf"][p, i])).max()
+
+
 @pytest.mark.parametrize("tag", ["c1", "ragged"])
 def test_oracle_loss_and_fd(golden, tag):
     g = golden("loss_cases.npz")
