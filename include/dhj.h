@@ -203,6 +203,15 @@ DHJ_API int dhj_generate(dhj_ctx* ctx, uint64_t seed, int64_t first, int64_t n, 
                          double r, int32_t N, double L, double* params, double* spots, double* model, double* market,
                          double* loss);
 
+/* ---- checked build -----------------------------------------------------------------------------
+ * lib/libdhj_checked.so is the same library compiled with -DDHJ_CHECKED: the kernels verify their own shared-memory
+ * protocol (a stage of coefficients read before it was written / overwritten before it was consumed, an item record
+ * used before it was prepared) and their shared / output indices, and count violations on the device (the substitute
+ * for compute-sanitizer, which is closed on the B200 pool).  counts[8]: violations per kind since the library was
+ * loaded (order: read-before-write, write-before-consumed, shared index, output index, item not prepared, 3 spare);
+ * *enabled = 0 and all zeros in the product build. */
+DHJ_API int dhj_debug_checks(dhj_ctx* ctx, int32_t* enabled, uint64_t* counts);
+
 /* ---- measurement ---------------------------------------------------------------------------- */
 /* Runs register-resident FP64 FMA-chain kernels on every SM (two operand forms: three vector registers, and one
  * multiplicand from a uniform register) and reports the best sustained DFMA rate (2 flop per FMA) — the

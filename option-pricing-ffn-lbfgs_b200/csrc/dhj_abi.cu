@@ -1062,6 +1062,23 @@ int dhj_generate(dhj_ctx* ctx, uint64_t seed, int64_t first, int64_t n, int32_t 
 
 extern "C" {
 
+// ---- checked build ---------------------------------------------------------------------------------
+int dhj_debug_checks(dhj_ctx* ctx, int32_t* enabled, uint64_t* counts) {
+  if (!ctx || !enabled || !counts) return fail(ctx, DHJ_ERR_ARG, "null argument");
+  for (int i = 0; i < kChkCodes; ++i) counts[i] = 0;
+#if defined(DHJ_CHECKED)
+  *enabled = 1;
+  DHJ_CUDA(ctx, cudaSetDevice(ctx->device));
+  DHJ_CUDA(ctx, cudaDeviceSynchronize());
+  unsigned long long host[kChkCodes];
+  DHJ_CUDA(ctx, cudaMemcpyFromSymbol(host, g_check_fail, sizeof(host)));
+  for (int i = 0; i < kChkCodes; ++i) counts[i] = host[i];
+#else
+  *enabled = 0;
+#endif
+  return DHJ_OK;
+}
+
 // ---- measurement -----------------------------------------------------------------------------
 int dhj_fp64_peak(dhj_ctx* ctx, int32_t iters, double* tflops, double* milliseconds) {
   if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");

@@ -52,6 +52,9 @@ struct ItemRec {
   unsigned valid_mask, bind_mask, call_mask;
   int o_lo;                        // first option (slice order) of the slice
   long long out_row;               // p * M
+#if defined(DHJ_CHECKED)
+  unsigned long long tag;          // batch that prepared the record
+#endif
 };
 
 // one warp's k-block of strike-independent coefficients P, Q, R.
@@ -61,6 +64,9 @@ struct ItemRec {
 struct CoefStage {
   Pair PQ[36];
   double R[40];
+#if defined(DHJ_CHECKED)
+  unsigned wtag[32], rtag[32], epoch;      // epoch of the last write per k slot / of the last read per lane / running epoch
+#endif
 };
 
 // pass of a strike whose +-0.1 widening binds: its own (a, b) and the rotation steps that go with it
@@ -84,6 +90,14 @@ struct PriceArgs;                  // dhj_kernels.cuh
 __device__ __forceinline__ void load_log_table(fm::Tables* dst, int tid) {
   if (tid < 64) { dst->log[tid] = fm::kTables.log[tid]; dst->exp2[tid] = fm::kTables.exp2[tid]; }
   if (tid < 65) dst->atan64[tid] = fm::kTables.atan64[tid];
+}
+
+// checked build: the stage's epoch bookkeeping starts at zero
+__device__ __forceinline__ void stage_check_init(CoefStage& st, int lane) {
+#if defined(DHJ_CHECKED)
+  st.wtag[lane] = 0u; st.rtag[lane] = 0u;
+  if (lane == 0) st.epoch = 0u;
+#endif
 }
 
 // u_1 = (1*pi)/(b-a), the rotation step's frequency (same correction step as u_of_k)
@@ -137,6 +151,11 @@ __device__ __forceinline__ void prepare_item(ItemRec& rec, const SliceView& v, c
   rec.valid_mask = (1u << cnt) - 1u;
   rec.bind_mask = bind; rec.call_mask = call;
   rec.o_lo = o_lo; rec.out_row = out_row;
+}
+__device__ __forceinline__ void tag_item(ItemRec& rec, unsigned long long batch_tag) {
+#if defined(DHJ_CHECKED)
+  rec.tag = batch_tag;
+#endif
 }
 
 // The quantities that are trigonometric functions of an angle LINEAR in k — the jump term's (cos, sin)(u_k mu)
@@ -192,11 +211,22 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
     if (any_put) a3 += c.P;
     if (blk == 0) g0_keep = __shfl_sync(kFullMask, c.g0, 0);
     __syncwarp();
+#if defined(DHJ_CHECKED)
+    const unsigned epoch = st.epoch + 1;                     // (same value in every lane: read between two barriers)
+    for (int l = 0; l < 32; ++l) DHJ_CHECK(st.rtag[l] == epoch - 1, kChkWriteBeforeConsumed);
+    DHJ_CHECK(slot_pq < 36 && slot_r < 40, kChkSharedIndex);
+    __syncwarp();
+    st.wtag[lane] = epoch;
+    if (lane == 0) st.epoch = epoch;
+#endif
     st.PQ[slot_pq] = make_double2(c.P, c.Q); st.R[slot_r] = c.R;
     __syncwarp();
     // task of this lane
     const int j = lane / kNumSeg, s = lane - j * kNumSeg;
     double val = 0.0;
+#if defined(DHJ_CHECKED)
+    for (int i = 0; i < kSeg; ++i) DHJ_CHECK(st.wtag[s * kSeg + i] == epoch, kChkReadBeforeWrite);
+#endif
     if ((mask >> j) & 1u) {
       if (exact) fm::sincos_(u_of_k(pc, k0 + s * kSeg) * (it.x[j] - pc.a), &sn, &cs);
       else rotate(cs, sn, c32[j], s32[j]);
@@ -208,6 +238,9 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
     val += __shfl_xor_sync(kFullMask, val, 1);
     val += __shfl_xor_sync(kFullMask, val, 2);
     acc += val;                                              // meaningful in the lanes (j, 0) of active strikes
+#if defined(DHJ_CHECKED)
+    st.rtag[lane] = epoch;
+#endif
   }
   // strike-independent sums of the pass, then the constant part of each strike
   const double A1 = any_call ? warp_sum(a1) : 0.0, A2 = any_call ? warp_sum(a2) : 0.0;
@@ -223,7 +256,8 @@ __device__ __forceinline__ void contract_pass(const ItemRec& it, const PassConst
 // barrier, no partial sums in shared memory; sink(i, j, item, price) receives each price from lane 4 j.
 // Strikes with their own (a, b) get an extra pass each (rare), set up by lane 0 in the warp's ExtraPass.
 template <class Smem, class Sink>
-__device__ __forceinline__ void run_batch(Smem& sm, const SliceView& v, int cnt_items, int tid, Sink sink) {
+__device__ __forceinline__ void run_batch(Smem& sm, const SliceView& v, int cnt_items, int tid,
+                                          unsigned long long batch_tag, Sink sink) {
   // the shuffle tells ptxas that the warp index is warp-uniform: the item loop and everything addressed through it
   // then run on the uniform datapath (constants via LDCU into uniform registers, address arithmetic off the
   // vector pipe)
@@ -232,6 +266,9 @@ __device__ __forceinline__ void run_batch(Smem& sm, const SliceView& v, int cnt_
 #pragma unroll 1
   for (int i = warp; i < cnt_items; i += kBatchWarps) {
     const ItemRec& it = sm.items[i];
+#if defined(DHJ_CHECKED)
+    DHJ_CHECK(it.tag == batch_tag, kChkItemNotPrepared);
+#endif
     double acc = 0.0;
     const unsigned reg_mask = it.valid_mask & ~it.bind_mask;
     if (reg_mask)

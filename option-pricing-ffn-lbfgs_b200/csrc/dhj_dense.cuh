@@ -97,8 +97,24 @@ __device__ __forceinline__ void dense_coefficients(DenseWarp& W, const PassConst
   a1 += c.a1; a2 += c.a2; a3 += c.P;
   if (k0 == 0) g0 = __shfl_sync(kFullMask, c.g0, 0);
   __syncwarp();                                        // the previous block's coefficients have been consumed
+#if defined(DHJ_CHECKED)
+  const unsigned epoch = W.stage.epoch + 1;
+  for (int l = 0; l < 32; ++l) DHJ_CHECK(W.stage.rtag[l] == epoch - 1, kChkWriteBeforeConsumed);
+  __syncwarp();
+  W.stage.wtag[lane] = epoch;
+  if (lane == 0) W.stage.epoch = epoch;
+#endif
   W.stage.PQ[lane] = make_double2(c.P, c.Q); W.stage.R[lane] = c.R;
   __syncwarp();
+#if defined(DHJ_CHECKED)
+  for (int l = 0; l < 32; ++l) DHJ_CHECK(W.stage.wtag[l] == epoch, kChkReadBeforeWrite);
+#endif
+}
+// checked build: this lane has finished reading the block's coefficients
+__device__ __forceinline__ void dense_consumed(DenseWarp& W, int lane) {
+#if defined(DHJ_CHECKED)
+  W.stage.rtag[lane] = W.stage.epoch;
+#endif
 }
 
 // regular pass: all strikes of the chunk whose widening does not bind, a lane per strike, rounds of 32
@@ -110,14 +126,27 @@ __device__ __forceinline__ void dense_pass(DenseWarp& W, int cnt, int n_cos, int
   for (int k0 = 0; k0 < n_cos; k0 += 32) {
     dense_coefficients(W, pc, k0, n_cos, lane, ltab, a1, a2, a3, g0);
     const double u0 = u_of_k(pc, k0);                   // frequency of the block's first term
+    // two strikes per lane and trip (t, t + 32) while both exist, then single strikes: the pair shares the
+    // coefficient loads and gives the pipe two independent chains
+    int t = lane;
 #pragma unroll 1
-    for (int t = lane; t < cnt; t += 32) {
-      if (W.bind[t]) continue;
+    for (; t + 32 < cnt; t += 64) {
+      const int tb = t + 32;
+      double sna, csa, snb, csb, spqa, sra, spqb, srb;
+      fm::sincos_(u0 * (W.x[t] - pc.a), &sna, &csa);
+      fm::sincos_(u0 * (W.x[tb] - pc.a), &snb, &csb);
+      segment_sums2<32>(W.stage.PQ, reinterpret_cast<const Pair*>(W.stage.R), csa, sna, W.cth[t], W.sth[t], csb, snb,
+                        W.cth[tb], W.sth[tb], &spqa, &sra, &spqb, &srb);
+      if (!W.bind[t]) W.part[t] += fma(W.K[t], sra, -(W.sex[t] * spqa));
+      if (!W.bind[tb]) W.part[tb] += fma(W.K[tb], srb, -(W.sex[tb] * spqb));
+    }
+    if (t < cnt && !W.bind[t]) {
       double sn, cs, spq, sr;
       fm::sincos_(u0 * (W.x[t] - pc.a), &sn, &cs);
       segment_sums<32>(W.stage.PQ, reinterpret_cast<const Pair*>(W.stage.R), cs, sn, W.cth[t], W.sth[t], &spq, &sr);
       W.part[t] += fma(W.K[t], sr, -(W.sex[t] * spq));
     }
+    dense_consumed(W, lane);
   }
   const double A1 = warp_sum(a1), A2 = warp_sum(a2), A3 = warp_sum(a3);
   for (int t = lane; t < cnt; t += 32)
@@ -149,6 +178,7 @@ __device__ __forceinline__ void dense_pass_single(DenseWarp& W, int t, int n_cos
     val += __shfl_xor_sync(kFullMask, val, 1);
     val += __shfl_xor_sync(kFullMask, val, 2);
     acc += val;                                        // meaningful in lane 0
+    dense_consumed(W, lane);
   }
   const double A1 = warp_sum(a1), A2 = warp_sum(a2), A3 = warp_sum(a3);
   if (lane == 0) W.part[t] = acc + strike_const_part(W.call[t] != 0, W.S0, W.K[t], W.x[t], pc, A1, A2, A3, g0);

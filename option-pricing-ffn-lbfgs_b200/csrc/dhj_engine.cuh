@@ -13,6 +13,21 @@ namespace dhj {
 
 constexpr unsigned kFullMask = 0xffffffffu;
 
+// ---- checked build (-DDHJ_CHECKED: lib/libdhj_checked.so, tests/test_gpu_checked.py) ---------------------------------
+// compute-sanitizer is closed on this pool, so the shared-memory protocol of the kernels is checked by the kernels
+// themselves in a separate build: every stage of coefficients carries the epoch it was written in and the epoch up to
+// which each lane has consumed it; a read before the matching write, a write before the readers are done, an index
+// outside a shared array or an output index outside the caller's buffer increments a device counter that the host
+// reads back (dhj_debug_checks).  The product build compiles the checks to nothing.
+enum CheckCode { kChkReadBeforeWrite = 0, kChkWriteBeforeConsumed = 1, kChkSharedIndex = 2, kChkOutputIndex = 3,
+                 kChkItemNotPrepared = 4, kChkCodes = 8 };
+#if defined(DHJ_CHECKED) && defined(__CUDACC__)
+__device__ unsigned long long g_check_fail[kChkCodes];
+#define DHJ_CHECK(cond, code) do { if (!(cond)) atomicAdd(&dhj::g_check_fail[code], 1ULL); } while (0)
+#else
+#define DHJ_CHECK(cond, code) do { } while (0)
+#endif
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(kFullMask, v, off);

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
   __shared__ PriceSmem sm;
   const int tid = threadIdx.x;
   load_log_table(&sm.ltab, tid);
+  stage_check_init(sm.stage[tid >> 5], tid & 31);
   const long long n_items = a.P * (long long)v.n_slices;
   const long long n_batches = (n_items + kPriceItems - 1) / kPriceItems;
   for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
@@ -49,11 +50,14 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
       const Params m = a.transform ? transform_params(pp) : load_params(pp);
       prepare_item(sm.items[tid], v, m, a.S0[row * a.s0_stride], v.strike + row * v.strike_stride, s,
                    p * (long long)v.n_options);
+      tag_item(sm.items[tid], (unsigned long long)batch + 1);
     }
     __syncthreads();
     // ---- phase 2: a warp per item, a lane per cosine index; the warp writes its prices -------------------
-    run_batch(sm, v, cnt_items, tid, [&](int, int j, const ItemRec& it, double price) {
-      a.out[it.out_row + v.pos[it.o_lo + j]] = price;
+    run_batch(sm, v, cnt_items, tid, (unsigned long long)batch + 1, [&](int, int j, const ItemRec& it, double price) {
+      const long long at = it.out_row + v.pos[it.o_lo + j];
+      DHJ_CHECK(at >= 0 && at < a.P * (long long)v.n_options, kChkOutputIndex);
+      a.out[at] = price;
     });
     __syncthreads();
   }
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(32 * kDenseWarps, DHJ_DENSE_MINB) k_price_dens
   DenseSmem& sm = *reinterpret_cast<DenseSmem*>(dense_smem_raw);
   const int tid = threadIdx.x;
   load_log_table(&sm.ltab, tid);
+  stage_check_init(sm.w[tid >> 5].stage, tid & 31);
   __syncthreads();
   const int warp = __shfl_sync(kFullMask, tid >> 5, 0), lane = tid & 31;
   DenseWarp& W = sm.w[warp];
@@ -109,7 +114,10 @@ __global__ void __launch_bounds__(32 * kDenseWarps, DHJ_DENSE_MINB) k_price_dens
         }
       }
       __syncwarp();
-      for (int t = lane; t < cnt; t += 32) out_row[v.pos[c_lo + t]] = W.disc * W.part[t];
+      for (int t = lane; t < cnt; t += 32) {
+        DHJ_CHECK(v.pos[c_lo + t] >= 0 && v.pos[c_lo + t] < v.n_options && t < kDenseChunk, kChkOutputIndex);
+        out_row[v.pos[c_lo + t]] = W.disc * W.part[t];
+      }
       __syncwarp();
     }
   }
@@ -139,6 +147,7 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_loss_batch(Sl
   __shared__ double s_feller[kPriceItems];
   const int tid = threadIdx.x;
   load_log_table(&sm.ltab, tid);
+  stage_check_init(sm.stage[tid >> 5], tid & 31);
   const int nS = v.n_slices;
   const long long n_batches = (a.n_units + a.units_per_batch - 1) / a.units_per_batch;
   for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
@@ -160,12 +169,16 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_loss_batch(Sl
       const Params m = transform_params(xv);
       const long long mi = a.market_index ? a.market_index[c] : 0;
       prepare_item(sm.items[tid], v, m, a.S0[mi], v.strike + mi * v.strike_stride, s, mi * (long long)v.n_options);
+      tag_item(sm.items[tid], (unsigned long long)batch + 1);
       if (s == 0) s_feller[ul] = feller_penalty(m);
     }
     __syncthreads();
     // ---- phase 2 (as k_price_batch): prices -> shared memory, in the item's ex[] slots (exp(x_j) is dead once
     // the item's passes are done; only the warp that owns the item touches them) -----------------------------
-    run_batch(sm, v, cnt_items, tid, [&](int i, int j, const ItemRec&, double price) { sm.items[i].ex[j] = price; });
+    run_batch(sm, v, cnt_items, tid, (unsigned long long)batch + 1, [&](int i, int j, const ItemRec&, double price) {
+      DHJ_CHECK(i >= 0 && i < kPriceItems && j >= 0 && j < kBatchMaxStrikes, kChkSharedIndex);
+      sm.items[i].ex[j] = price;
+    });
     __syncthreads();
     // ---- phase 4: one thread per unit: loss, and the gradient when a state's stencil is complete ----------
     if (tid < n_units_here) {

@@ -397,6 +397,42 @@ DHJ_HD void segment_sums(const Pair* __restrict__ PQ, const Pair* __restrict__ R
   *sum_pq = apq; *sum_r = ar;
 }
 
+// The same for TWO strikes at once (dense kernel): the coefficient loads are shared and the two recurrences are
+// independent chains, which is what the FP64 pipe needs to stay busy with few warps.  Same operations per strike as
+// segment_sums: same bits.
+template <int SEG>
+DHJ_HD void segment_sums2(const Pair* __restrict__ PQ, const Pair* __restrict__ RR, double ca, double sa, double ctha,
+                          double stha, double cb, double sb, double cthb, double sthb, double* sum_pq_a,
+                          double* sum_r_a, double* sum_pq_b, double* sum_r_b) {
+  Pair pq = PQ[0], rr = RR[0];
+  double apqa = fma(pq.y, sa, pq.x * ca), ara = rr.x * sa;
+  double apqb = fma(pq.y, sb, pq.x * cb), arb = rr.x * sb;
+  double c1a = fma(ca, ctha, -(sa * stha)), s1a = fma(sa, ctha, ca * stha);
+  double c1b = fma(cb, cthb, -(sb * sthb)), s1b = fma(sb, cthb, cb * sthb);
+  const double two_ca = ctha + ctha, two_cb = cthb + cthb;
+  pq = PQ[1];
+  apqa = fma(pq.x, c1a, apqa); apqa = fma(pq.y, s1a, apqa); ara = fma(rr.y, s1a, ara);
+  apqb = fma(pq.x, c1b, apqb); apqb = fma(pq.y, s1b, apqb); arb = fma(rr.y, s1b, arb);
+#pragma unroll
+  for (int i = 2; i < SEG; i += 2) {
+    double c2a = fma(two_ca, c1a, -ca), s2a = fma(two_ca, s1a, -sa);
+    double c2b = fma(two_cb, c1b, -cb), s2b = fma(two_cb, s1b, -sb);
+    ca = c1a; sa = s1a; c1a = c2a; s1a = s2a;
+    cb = c1b; sb = s1b; c1b = c2b; s1b = s2b;
+    pq = PQ[i]; rr = RR[i >> 1];
+    apqa = fma(pq.x, c1a, apqa); apqa = fma(pq.y, s1a, apqa); ara = fma(rr.x, s1a, ara);
+    apqb = fma(pq.x, c1b, apqb); apqb = fma(pq.y, s1b, apqb); arb = fma(rr.x, s1b, arb);
+    c2a = fma(two_ca, c1a, -ca); s2a = fma(two_ca, s1a, -sa);
+    c2b = fma(two_cb, c1b, -cb); s2b = fma(two_cb, s1b, -sb);
+    ca = c1a; sa = s1a; c1a = c2a; s1a = s2a;
+    cb = c1b; sb = s1b; c1b = c2b; s1b = s2b;
+    pq = PQ[i + 1];
+    apqa = fma(pq.x, c1a, apqa); apqa = fma(pq.y, s1a, apqa); ara = fma(rr.y, s1a, ara);
+    apqb = fma(pq.x, c1b, apqb); apqb = fma(pq.y, s1b, apqb); arb = fma(rr.y, s1b, arb);
+  }
+  *sum_pq_a = apqa; *sum_r_a = ara; *sum_pq_b = apqb; *sum_r_b = arb;
+}
+
 // strike-dependent constant part (uses warp- or block-level sums A1, A2, A3, g0: it is linear in them)
 DHJ_HD double strike_const_part(bool is_call, double S0, double K, double x, const PassConsts& p, double A1,
                                 double A2, double A3, double g0) {

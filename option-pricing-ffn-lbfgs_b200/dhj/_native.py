@@ -25,7 +25,7 @@ EXPORTS = (
     "dhj_market_create", "dhj_market_destroy", "dhj_loss_batch", "dhj_loss_fd", "dhj_market_prices",
     "dhj_cf", "dhj_cf_complex", "dhj_truncation_range", "dhj_chi_psi", "dhj_fp64_peak",
     "dhj_lbfgs_create", "dhj_lbfgs_destroy", "dhj_lbfgs_ask", "dhj_lbfgs_tell", "dhj_lbfgs_result",
-    "dhj_generator_draws", "dhj_generate_dev", "dhj_generate", "dhj_set_host_threads",
+    "dhj_generator_draws", "dhj_generate_dev", "dhj_generate", "dhj_set_host_threads", "dhj_debug_checks",
 )
 
 
@@ -101,6 +101,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.dhj_generate_dev.argtypes = gen_head + [_c_vp] * 6
         lib.dhj_generate.argtypes = gen_head + [_c_vp] * 5
         lib.dhj_set_host_threads.argtypes = [_c_i32]
+        lib.dhj_debug_checks.argtypes = [_c_vp, ctypes.POINTER(_c_i32), ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")]
         for name in EXPORTS:
             if name not in ("dhj_last_error",):
                 getattr(lib, name).restype = ctypes.c_int
@@ -125,8 +126,10 @@ def _ptr(a: np.ndarray) -> int:
 class Context:
     """One libdhj context = one CUDA device.  Calls are serialised with a lock (the C side is not re-entrant)."""
 
-    def __init__(self, device: int = 0):
-        self._lib = load_library()
+    def __init__(self, device: int = 0, library: str | None = None):
+        """`library`: path of another build of libdhj (the checked build of tests/test_gpu_checked.py); default the
+        product library."""
+        self._lib = load_library(library)
         self._h = _c_vp()
         self._lock = threading.RLock()
         rc = self._lib.dhj_init(int(device), ctypes.byref(self._h))
@@ -151,6 +154,13 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def debug_checks(self):
+        """(enabled, counts[8]) of the checked build's device-side self-checks (dhj_debug_checks)."""
+        en, counts = _c_i32(), np.zeros(8, dtype=np.uint64)
+        with self._lock:
+            self._check(self._lib.dhj_debug_checks(self._h, ctypes.byref(en), counts), "dhj_debug_checks")
+        return bool(en.value), counts
 
     @property
     def launch_count(self) -> int:

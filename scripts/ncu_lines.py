@@ -18,8 +18,12 @@ for r in csv.reader(io.StringIO(txt)):
     elif len(r) > 5 and r[0] == "Line No":
         hdr = {h: i for i, h in enumerate(r)}
     elif hdr and len(r) > 5 and r[0]:
-        rows.append((fname, int(r[0]), r[1].strip(), int(r[hdr["Instructions Executed"]]),
-                     int(r[hdr["# Samples"]])))
+        def num(v):
+            try:
+                return int(v)
+            except ValueError:
+                return 0
+        rows.append((fname, int(r[0]), r[1].strip(), num(r[hdr["Instructions Executed"]]), num(r[hdr["# Samples"]])))
 tot_i = sum(r[3] for r in rows)
 tot_s = sum(r[4] for r in rows)
 print(f"total warp instructions {tot_i}, samples {tot_s}")
