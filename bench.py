@@ -355,7 +355,9 @@ class ClockSampler:
 def bind_rank_to_cores(local: int, world: int):
     """With several ranks on one host, give each rank its own slice of the cores NVML names as near its GPU (before
     any pinned allocation: first touch decides the memory node).  Returns a description for the JSON line."""
-    if world <= 1 or os.environ.get("BENCH_NO_BIND"):
+    # opt-in (BENCH_BIND=1): on this pool's 8-GPU hosts every GPU reports the same 32 cores and one memory node, and
+    # slicing them per rank made the end-to-end arm 2 % slower (8.98e9 vs 9.15e9 prices/s, profiles/README.md r02)
+    if world <= 1 or not os.environ.get("BENCH_BIND"):
         return None
     try:
         import pynvml

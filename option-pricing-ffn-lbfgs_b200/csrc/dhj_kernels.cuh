@@ -41,12 +41,25 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(S
     const long long base = batch * kPriceItems;
     const int cnt_items = (int)min((long long)kPriceItems, n_items - base);
     // ---- phase 1: one thread per item ----------------------------------------------------------
+#if defined(DHJ_COALESCED_PARAMS)
+    // (experiment, profiles/README.md r02: the batch's parameter rows, contiguous in global memory, swept into shared
+    // memory by all 128 threads with coalesced loads, then read per item from there)
+    __shared__ double s_params[(kPriceItems + 2) * kNumParams];
+    const long long p_first = base / v.n_slices, p_last = (base + cnt_items - 1) / v.n_slices;
+    const int n_rows = (int)(p_last - p_first + 1);
+    for (int e = tid; e < n_rows * kNumParams; e += kBatchThreads) s_params[e] = a.params[p_first * kNumParams + e];
+    __syncthreads();
+#endif
     if (tid < cnt_items) {
       const long long item = base + tid;
       const long long p = item / v.n_slices;
       const int s = (int)(item - p * v.n_slices);
       const long long row = a.row_index ? (long long)a.row_index[p] : p;
+#if defined(DHJ_COALESCED_PARAMS)
+      const double* pp = s_params + (p - p_first) * kNumParams;
+#else
       const double* pp = a.params + kNumParams * p;
+#endif
       const Params m = a.transform ? transform_params(pp) : load_params(pp);
       prepare_item(sm.items[tid], v, m, a.S0[row * a.s0_stride], v.strike + row * v.strike_stride, s,
                    p * (long long)v.n_options);
