@@ -157,6 +157,13 @@ DHJ_API int dhj_lbfgs_tell(dhj_lbfgs* opt, int64_t n_active, const double* f, co
 /* any output may be NULL: x[n][dim], f[n], nit[n], nfev[n], status[n] */
 DHJ_API int dhj_lbfgs_result(const dhj_lbfgs* opt, double* x, double* f, int32_t* nit, int32_t* nfev, int32_t* status);
 
+/* The whole lock-step loop in one call (what dhj.calibrate_many runs per pipeline): ask -> dhj_loss_fd over every
+ * state that waits for an evaluation, state i on market state_market[i] (NULL: market 0) -> tell, until all n_states
+ * optimisers of `opt` have stopped.  rounds = launches, state_rounds = sum of evaluated states over the rounds,
+ * seconds[3] = host time in ask / in the loss calls (copies + launch + wait) / in tell.  Outputs may be NULL. */
+DHJ_API int dhj_lbfgs_minimize_fd(dhj_lbfgs* opt, dhj_ctx* ctx, const dhj_market* market, const int32_t* state_market,
+                                  int64_t n_states, double h, int64_t* rounds, int64_t* state_rounds, double* seconds);
+
 /* Threads used by the library's host-side parallel loops (optimiser states in ask / tell, staging copies of pageable
  * buffers); 0 = all cores (default).  Several lock-step pipelines on one host divide the cores with this. */
 DHJ_API int dhj_set_host_threads(int32_t n);

@@ -223,13 +223,37 @@ bool is_pinned_host(const void* p) {
   return at.type == cudaMemoryTypeHost;
 }
 
-// k_price_batch handles slices of <= 8 strikes (warp per item, lane per k, 32 items per block); k_price_dense the rest
-int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_slice, cudaStream_t st);
+// Batch size of the batch engine for a launch of `n_units` units of `items_per_unit` items each (pricing: unit = item).
+// A block's time is its phase 1 (one warp, ~0.9 item times) plus that of its busiest warp (items are dealt to the four
+// warps in turn); a launch's time is the number of waves of resident blocks times that.  Minimise
+// waves x (0.9 + ceil(items per batch / 4)) over whole units per batch; ties go to the larger batch.  E.g. 7 000 loss
+// evaluations of a 3-slice market: 10 units per batch = 700 blocks = 2 waves (the second nearly empty) of 8 items per
+// warp, 4 units per batch = 3 waves of 3.  Large launches end at full batches, a single calibration at one unit per
+// block (every unit on its own SM: latency).
+int pick_units_per_batch(long long n_units, int items_per_unit, int max_items, long long resident_blocks) {
+  const int upb_max = std::max(1, max_items / std::max(1, items_per_unit));
+  long long best_cost = -1;
+  int best = 1;
+  for (int upb = upb_max; upb >= 1; --upb) {
+    const long long blocks = (n_units + upb - 1) / upb;
+    const long long waves = (blocks + resident_blocks - 1) / resident_blocks;
+    const long long cost = waves * (9 + 10 * (((long long)upb * items_per_unit + kBatchWarps - 1) / kBatchWarps));
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = upb; }
+  }
+  return best;
+}
 
-int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_slice, cudaStream_t st) {
+// k_price_batch handles slices of <= 8 strikes (warp per item, lane per k, <= 32 items per block); k_price_dense the rest
+int launch_price(dhj_ctx* ctx, const SliceView& v, PriceArgs a, int max_slice, cudaStream_t st);
+
+int launch_price(dhj_ctx* ctx, const SliceView& v, PriceArgs a, int max_slice, cudaStream_t st) {
   const long long items = a.P * (long long)v.n_slices;
   if (max_slice <= kBatchMaxStrikes) {
-    const long long batches = (items + kPriceItems - 1) / kPriceItems;
+    // full batches of 32 items unless the launch is only a few waves long (mid-size loss rounds through the split path)
+    const long long resident = (long long)ctx->sm_count * ctx->loss_blocks_per_sm;
+    a.items_per_batch = (items > 64 * resident * kPriceItems) ? kPriceItems
+                                                              : pick_units_per_batch(items, 1, kPriceItems, resident);
+    const long long batches = (items + a.items_per_batch - 1) / a.items_per_batch;
     // one block per batch: the hardware block scheduler balances the SMs dynamically (a persistent grid with a
     // static batch -> block map measured ~3 % slower: the slowest SM sets the time)
     const long long cap = 2147483647LL;
@@ -238,10 +262,12 @@ int launch_price(dhj_ctx* ctx, const SliceView& v, const PriceArgs& a, int max_s
     static const size_t extra = [] {
       const char* e = getenv("DHJ_DEBUG_EXTRA_SMEM");
       size_t b = e ? (size_t)atol(e) : 0;
-      if (b) cudaFuncSetAttribute(k_price_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b);
+      if (b) cudaFuncSetAttribute(k_price_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b);
       return b;
     }();
-    k_price_batch<<<(int)std::max<long long>(1, std::min(batches, cap)), kBatchThreads, extra, st>>>(v, a);
+    const int grid = (int)std::max<long long>(1, std::min(batches, cap));
+    if (a.items_per_batch == kPriceItems) k_price_batch<true><<<grid, kBatchThreads, extra, st>>>(v, a);
+    else k_price_batch<false><<<grid, kBatchThreads, 0, st>>>(v, a);
   } else {
     // a warp per item, four items per block; the block's shared memory (four private strike tables) exceeds the
     // 48 KB static limit: opt in once
@@ -692,11 +718,9 @@ static int run_loss(dhj_ctx* ctx, const dhj_market* mk, const double* x, const i
     a.market = (const double*)mk->d_price.p; a.fd = fd; a.h = h; a.n_units = n_units;
     a.f_all = (double*)ctx->d_f.p; a.fg = fd ? (double*)ctx->d_fg.p : nullptr;
     a.counters = fd ? (unsigned int*)ctx->d_counters.p : nullptr;
-    // whole units per block batch; few units (one calibration) -> one unit per block so that every unit
-    // runs on its own SM (latency), many units -> full batches of kPriceItems items (throughput)
-    const int upb_max = std::max(1, kPriceItems / v.n_slices);
-    const long long resident = (long long)ctx->sm_count * ctx->loss_blocks_per_sm;
-    a.units_per_batch = (int)std::max<long long>(1, std::min<long long>(upb_max, n_units / resident));
+    // whole units per block batch (pick_units_per_batch: waves x block time)
+    a.units_per_batch = pick_units_per_batch(n_units, v.n_slices, kPriceItems,
+                                             (long long)ctx->sm_count * ctx->loss_blocks_per_sm);
     const long long batches = (n_units + a.units_per_batch - 1) / a.units_per_batch;
     k_loss_batch<<<(int)std::max<long long>(1, std::min(batches, 2147483647LL)), kBatchThreads, 0, ctx->stream>>>(v, a);
     DHJ_CUDA(ctx, cudaGetLastError());
@@ -756,6 +780,48 @@ int dhj_loss_fd(dhj_ctx* ctx, const dhj_market* market, const double* x, const i
   if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
   if (!(h > 0.0)) return fail(ctx, DHJ_ERR_ARG, "h must be > 0");
   return run_loss(ctx, market, x, market_index, C, 1, h, out_f, out_g, out_f_all);
+}
+
+// The whole lock-step loop of many simultaneous calibrations in one call: ask -> one loss / forward-difference
+// launch over every state that waits for an evaluation -> tell, until every optimiser has stopped.  (The Python
+// host used to drive the three steps itself; with several pipelines per GPU their interpreter work serialised on
+// the GIL — in here a pipeline never touches it.)
+int dhj_lbfgs_minimize_fd(dhj_lbfgs* opt, dhj_ctx* ctx, const dhj_market* market, const int32_t* state_market,
+                          int64_t n_states, double h, int64_t* rounds, int64_t* state_rounds, double* seconds) {
+  if (!ctx) return fail(nullptr, DHJ_ERR_ARG, "null context");
+  if (!opt || !market) return fail(ctx, DHJ_ERR_ARG, "null optimiser or market");
+  if (n_states < 0) return fail(ctx, DHJ_ERR_ARG, "n_states must be >= 0");
+  if (!(h > 0.0)) return fail(ctx, DHJ_ERR_ARG, "h must be > 0");
+  std::vector<int64_t> idx((size_t)n_states);
+  std::vector<int32_t> mi((size_t)n_states);
+  std::vector<double> x((size_t)n_states * kNumParams), f((size_t)n_states), g((size_t)n_states * kNumParams);
+  int64_t n_rounds = 0, n_state_rounds = 0;
+  double t_ask = 0.0, t_loss = 0.0, t_tell = 0.0;
+  for (;;) {
+    const double t0 = omp_get_wtime();
+    int64_t na = 0;
+    int rc = dhj_lbfgs_ask(opt, &na, idx.data(), x.data());
+    if (rc) return fail(ctx, rc, "dhj_lbfgs_ask failed (%d)", rc);
+    if (na > n_states) return fail(ctx, DHJ_ERR_ARG, "the optimiser holds more states (%lld) than n_states", (long long)na);
+    const double t1 = omp_get_wtime();
+    t_ask += t1 - t0;
+    if (na == 0) break;
+    if (state_market)
+      for (int64_t a = 0; a < na; ++a) mi[a] = state_market[idx[a]];
+    rc = run_loss(ctx, market, x.data(), state_market ? mi.data() : nullptr, na, 1, h, f.data(), g.data(), nullptr);
+    if (rc) return rc;
+    const double t2 = omp_get_wtime();
+    rc = dhj_lbfgs_tell(opt, na, f.data(), g.data());
+    if (rc) return fail(ctx, rc, "dhj_lbfgs_tell failed (%d)", rc);
+    t_loss += t2 - t1;
+    t_tell += omp_get_wtime() - t2;
+    ++n_rounds;
+    n_state_rounds += na;
+  }
+  if (rounds) *rounds = n_rounds;
+  if (state_rounds) *state_rounds = n_state_rounds;
+  if (seconds) { seconds[0] = t_ask; seconds[1] = t_loss; seconds[2] = t_tell; }
+  return DHJ_OK;
 }
 
 int dhj_market_prices(dhj_ctx* ctx, const dhj_market* mk, const double* x, const int32_t* market_index,

@@ -27,19 +27,24 @@ struct PriceArgs {
   long long P;
   int transform;
   double* out;               // [P][M]
+  int items_per_batch;       // <= kPriceItems; set by launch_price
 };
 
 // Slices of <= 8 strikes: see dhj_batch.cuh.
+// FULL: batches of kPriceItems items (a compile-time constant: large launches); otherwise a.items_per_batch, chosen per
+// launch for mid-size launches that are only a few waves of blocks long (launch_price)
+template <bool FULL>
 __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_price_batch(SliceView v, PriceArgs a) {
   __shared__ PriceSmem sm;
   const int tid = threadIdx.x;
   load_log_table(&sm.ltab, tid);
   stage_check_init(sm.stage[tid >> 5], tid & 31);
   const long long n_items = a.P * (long long)v.n_slices;
-  const long long n_batches = (n_items + kPriceItems - 1) / kPriceItems;
+  const int ipb = FULL ? kPriceItems : a.items_per_batch;
+  const long long n_batches = (n_items + ipb - 1) / ipb;
   for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-    const long long base = batch * kPriceItems;
-    const int cnt_items = (int)min((long long)kPriceItems, n_items - base);
+    const long long base = batch * ipb;
+    const int cnt_items = (int)min((long long)ipb, n_items - base);
     // ---- phase 1: one thread per item ----------------------------------------------------------
 #if defined(DHJ_COALESCED_PARAMS)
     // (experiment, profiles/README.md r02: the batch's parameter rows, contiguous in global memory, swept into shared

@@ -24,7 +24,7 @@ EXPORTS = (
     "dhj_price_list", "dhj_price_grid", "dhj_price_grid_dev",
     "dhj_market_create", "dhj_market_destroy", "dhj_loss_batch", "dhj_loss_fd", "dhj_market_prices",
     "dhj_cf", "dhj_cf_complex", "dhj_truncation_range", "dhj_chi_psi", "dhj_fp64_peak",
-    "dhj_lbfgs_create", "dhj_lbfgs_destroy", "dhj_lbfgs_ask", "dhj_lbfgs_tell", "dhj_lbfgs_result",
+    "dhj_lbfgs_create", "dhj_lbfgs_destroy", "dhj_lbfgs_ask", "dhj_lbfgs_tell", "dhj_lbfgs_result", "dhj_lbfgs_minimize_fd",
     "dhj_generator_draws", "dhj_generate_dev", "dhj_generate", "dhj_set_host_threads", "dhj_debug_checks",
 )
 
@@ -91,6 +91,8 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
         lib.dhj_lbfgs_ask.argtypes = [_c_vp, ctypes.POINTER(_c_i64), _I64, _F64]
         lib.dhj_lbfgs_tell.argtypes = [_c_vp, _c_i64, _F64, _F64]
         lib.dhj_lbfgs_result.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]
+        lib.dhj_lbfgs_minimize_fd.argtypes = [_c_vp, _c_vp, _c_vp, _c_vp, _c_i64, _c_f64, ctypes.POINTER(_c_i64),
+                                              ctypes.POINTER(_c_i64), _F64]
         _U32 = ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
         lib.dhj_generator_draws.argtypes = [_U32, _c_i32, _c_i32, _c_f64, _c_i64, _c_i32, _F64, _F64, _c_f64, _c_f64,
                                             _c_f64, _c_f64, _c_f64, _c_i32, _F64, _F64, _F64, _U32,
@@ -449,6 +451,20 @@ class BatchLBFGS:
         rc = self._lib.dhj_lbfgs_tell(self._h, self._n_active, f, g)
         if rc != 0:
             raise NativeError(f"dhj_lbfgs_tell failed ({rc})")
+
+    def minimize_fd(self, market: "Market", state_market=None, h=1e-8):
+        """Run the whole lock-step loop natively (dhj_lbfgs_minimize_fd): every round one `dhj_loss_fd` launch on
+        `market` over all states that wait for an evaluation (state i uses market `state_market[i]`), until every
+        optimiser has stopped.  Returns (rounds, state_rounds, (seconds in ask, loss, tell)).  The GIL is released for
+        the whole call."""
+        sm = None if state_market is None else np.ascontiguousarray(np.asarray(state_market, dtype=np.int32).reshape(self.n))
+        rounds, state_rounds, secs = _c_i64(), _c_i64(), np.zeros(3)
+        c = market.ctx
+        with c._lock:
+            c._check(self._lib.dhj_lbfgs_minimize_fd(self._h, c._h, market._h, None if sm is None else sm.ctypes.data,
+                                                     self.n, float(h), ctypes.byref(rounds), ctypes.byref(state_rounds),
+                                                     secs), "dhj_lbfgs_minimize_fd")
+        return rounds.value, state_rounds.value, tuple(secs)
 
     def result(self):
         x, f = np.empty((self.n, self.dim)), np.empty(self.n)

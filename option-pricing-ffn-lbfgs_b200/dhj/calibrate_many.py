@@ -87,14 +87,15 @@ _pipeline_contexts: list = []       # second context (own stream and staging) fo
 
 def default_pipelines() -> int:
     """Host pipelines for large batches: enough to keep the GPU busy while other pipelines' host optimisers work
-    (measured on one B200, 10 000 markets x 3 starts: 1 pipeline 0.76 s, 2: 0.68, 4: 0.55, 6: 0.55; 1 250 markets:
-    0.146 / 0.132 / 0.111 / 0.126 s), bounded by
-    the cores this process may use (a rank of a multi-GPU job is bound to its share of the host)."""
+    (measured on one B200 with the native lock-step loop, 10 000 markets x 3 starts: 1 pipeline 0.72 s, 2: 0.64,
+    4: 0.55, 6: 0.52 — the GPU-side floor is 0.45 s; 1 250 markets: 0.132 / 0.113 / 0.092 / 0.088 s), bounded by this
+    process's share of the host's cores (torchrun's LOCAL_WORLD_SIZE ranks share them)."""
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    return max(1, min(4, cores // 2))
+    ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(6, cores // (2 * ranks_here)))
 
 
 def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, maxiter=300, multi_start=3,
@@ -129,25 +130,11 @@ def calibrate_many(spots, risk_free_rate, strikes, maturities, is_call, prices, 
     market = ctx.market(spots, risk_free_rate, strikes, maturities, is_call, prices)
     state_market = np.repeat(np.arange(n, dtype=np.int32), multi_start)
     opt = BatchLBFGS(x0, maxiter=maxiter, ftol=1e-9, gtol=1e-6)
-    rounds, active_sum = 0, 0
-    t_ask = t_loss = t_tell = 0.0
     clock = time.perf_counter
     t_loop0 = clock()
     t_setup = time.time() - t0
-    while True:
-        ta = clock()
-        idx, x = opt.ask()
-        tb = clock()
-        t_ask += tb - ta
-        if idx.size == 0:
-            break
-        f, g = market.loss_fd(x, 1e-8, market_index=state_market[idx])
-        tc = clock()
-        opt.tell(f, g)
-        t_loss += tc - tb
-        t_tell += clock() - tc
-        rounds += 1
-        active_sum += idx.size
+    # the lock-step loop (ask -> one loss / FD launch over all running states -> tell) runs natively, GIL released
+    rounds, active_sum, (t_ask, t_loss, t_tell) = opt.minimize_fd(market, state_market, 1e-8)
     t_loop1 = clock()
     xs, fs, nit, nfev, status = opt.result()
     opt.close()
