@@ -576,10 +576,10 @@ def run_sweep(B: Bench, wl, steps, warmup):
     drawn, priced, noised and reduced to losses on the device; the per-sample losses are all-gathered inside the
     timed region (prices and market prices stay sharded, as a dataset writer would leave them)."""
     torch, ctx, dist = B.torch, B.ctx, B.dist
-    from dhj.shard import shard_bounds
+    from dhj.shard import history_shard
     n_total, path_len = wl["P"], GEN["path_len"]
-    q_lo, q_hi = shard_bounds(-(-n_total // path_len), B.world, B.rank)
-    first, n = min(n_total, q_lo * path_len), min(n_total, q_hi * path_len) - min(n_total, q_lo * path_len)
+    first, hi_i = history_shard(n_total, path_len, B.world, B.rank)
+    n = hi_i - first
     per = -(-(-(-n_total // path_len)) // B.world) * path_len                 # padded block of the gather
     M = 15
     f64 = dict(dtype=torch.float64, device=B.dev)

@@ -19,6 +19,16 @@ def shard_bounds(n_items: int, world: int, rank: int) -> tuple[int, int]:
     return lo, min(n_items, lo + per)
 
 
+def history_shard(n_samples: int, path_len: int, world: int, rank: int) -> tuple[int, int]:
+    """[lo, hi) sample range of rank `rank` when a counter-stream dataset of `n_samples` samples is split by whole
+    histories of `path_len` samples (`shard_bounds` over histories; the last history may be partial)."""
+    if path_len < 1:
+        raise ValueError("path_len must be >= 1")
+    n_paths = -(-n_samples // path_len) if n_samples else 0
+    q_lo, q_hi = shard_bounds(n_paths, world, rank)
+    return min(n_samples, q_lo * path_len), min(n_samples, q_hi * path_len)
+
+
 def _dist():
     # importing torch costs seconds: only look for a process group if somebody already imported it
     import sys

@@ -200,13 +200,11 @@ def generate_synthetic_arrays(n_samples, ctx=None, save_path=None, *, seed=None,
     n_samples, path_len, first = int(n_samples), int(path_len), int(first)
     rank = world = None
     if sharded:
-        from dhj.shard import _dist, shard_bounds
+        from dhj.shard import _dist, history_shard
         dist = _dist()
         world = dist.get_world_size(group) if dist else 1
         rank = dist.get_rank(group) if dist else 0
-        n_paths = -(-n_samples // path_len)
-        q_lo, q_hi = shard_bounds(n_paths, world, rank)
-        lo_i, hi_i = min(n_samples, q_lo * path_len), min(n_samples, q_hi * path_len)
+        lo_i, hi_i = history_shard(n_samples, path_len, world, rank)
         first, n_samples = first + lo_i, hi_i - lo_i
     lo = np.array([v[0] for v in PARAM_RANGES.values()])
     hi = np.array([v[1] for v in PARAM_RANGES.values()])

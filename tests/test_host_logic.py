@@ -254,6 +254,20 @@ def test_shard_bounds():
         shard_bounds(10, 2, 2)
 
 
+def test_history_shards_cover_the_dataset():
+    """Counter-stream datasets are split by whole histories: the ranks' ranges are disjoint, ordered, cover [0, n) and cut
+    only at history boundaries (except the dataset's end)."""
+    from dhj.shard import history_shard
+    for n, path_len in ((100_000_000, 500), (1500, 500), (1499, 500), (7, 500), (0, 500), (1000, 1), (12345, 7)):
+        for w in (1, 2, 3, 8):
+            blocks = [history_shard(n, path_len, w, r) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            assert all(lo % path_len == 0 for lo, hi in blocks if lo < n)
+            assert all(hi % path_len == 0 or hi == n for lo, hi in blocks)
+    assert history_shard(100_000_000, 500, 8, 3) == (37_500_000, 50_000_000)
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, ROOT); sys.path.insert(0, PKG)
@@ -274,13 +288,26 @@ def _gloo_worker(rank, world, port, q):
     local, (lo, hi) = price_grid_sharded(fake_ctx_price_grid, params, spots, O2.GENERATOR_STRIKES_REL,
                                          O2.GENERATOR_MATURITIES, 0.03, gather=False)
     want = fake_ctx_price_grid(params, spots, O2.GENERATOR_STRIKES_REL, O2.GENERATOR_MATURITIES, 0.03)
+    # the dataset sweep's sharding (C4): every rank draws ITS histories of the counter stream (the oracle's restatement
+    # stands in for the device here), the gathered union equals the stream drawn in one piece
+    from dhj.shard import gather_rows, history_shard
+    n_ds, path_len = 1300, 500                                # 3 histories over 2 ranks: 1000 + 300 samples
+    s_lo, s_hi = history_shard(n_ds, path_len, world, rank)
+    mine = O2.counter_draws(11, s_lo, s_hi - s_lo, path_len)[0]
+    per = -(-3 // world) * path_len                           # padded block of the gather
+    padded = np.zeros((per, 13)); padded[:mine.shape[0]] = mine
+    gathered = gather_rows(padded, per * world)
+    whole = O2.counter_draws(11, 0, n_ds, path_len)[0]
+    union = np.concatenate([gathered[r * per:r * per + (hi_r - lo_r)]
+                            for r in range(world) for lo_r, hi_r in [history_shard(n_ds, path_len, world, r)]])
     q.put((rank, bool(np.array_equal(full, want)), bool(np.array_equal(local, want[lo:hi])),
-           (lo, hi) == shard_bounds(P, world, rank)))
+           (lo, hi) == shard_bounds(P, world, rank) and bool(np.array_equal(union, whole))))
     dist.destroy_process_group()
 
 
 def test_sharded_pricing_gloo_world2():
-    """world_size-2 gloo run of the N>1 path: block sharding by parameter set + all_gather of prices."""
+    """world_size-2 gloo run of the N>1 paths: block sharding by parameter set + all_gather of prices, and the dataset
+    sweep's sharding by whole histories of the counter stream."""
     import socket
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
