@@ -31,6 +31,7 @@ struct DenseWarp {
   SetConsts set;
   PassConsts pass, extra_pass;
   double S0, disc, a0, b0;
+  double jrot[3], extra_jrot[3];                   // jump recurrences of the regular / extra pass: cos, sin(32 u_1 mu), exp(-2048 alpha)
   double extra_cth, extra_sth;
   CoefStage stage;
   double K[kDenseChunk], x[kDenseChunk], sex[kDenseChunk], cth[kDenseChunk], sth[kDenseChunk];   // sex = S0 exp(x)
@@ -82,18 +83,41 @@ __device__ __forceinline__ void dense_prepare(DenseWarp& W, const SliceView& v, 
     W.pass.eb = fm::exp_(b0);
   } else if (lane == 2) {
     W.pass.ea = fm::exp_(a0);
+  } else if (lane == 3) {
+    PassConsts pc;                                   // the two fields u_one() reads
+    pc.w = b0 - a0; pc.rw = fm::rcp(pc.w);
+    jump_rotation(pc, m.mu, &W.jrot[0], &W.jrot[1]);
+    W.jrot[2] = fm::exp_neg(-2048.0 * jump_alpha(pc, 0.5 * (m.sj * m.sj)));
   }
 }
 
+// loop-carried state of the jump term's recurrences over the blocks of one pass (as in the batch kernel's
+// contract_pass: exact every kReseed blocks, a rotation / two products in between)
+struct JumpState { double cj = 1.0, sj = 0.0, ej = 1.0, rho = 1.0; };
+
 // CF at this lane's k of the block [k0, k0 + 32) -> strike-independent coefficients in the warp's stage; the lanes'
 // shares of A1, A2, A3 accumulate in a1, a2, a3; g0 (k = 0 only) is broadcast in the first block
-__device__ __forceinline__ void dense_coefficients(DenseWarp& W, const PassConsts& pc, int k0, int n_cos, int lane,
+__device__ __forceinline__ void dense_coefficients(DenseWarp& W, const PassConsts& pc, const double* __restrict__ jrot,
+                                                   JumpState& js, int k0, int n_cos, int lane,
                                                    const fm::Tables* __restrict__ ltab, double& a1, double& a2,
                                                    double& a3, double& g0) {
   const int k = k0 + lane;
-  KCoef c;
-  c.P = c.Q = c.R = c.a1 = c.a2 = c.g0 = 0.0;
-  if (k < n_cos) c = make_kcoef(make_kterm(W.set, pc, k, ltab), pc, k);
+  const bool exact = ((k0 >> 5) % kReseed) == 0;        // uniform
+  const double u = u_of_k(pc, k);
+  KTerm t = make_kterm_f(W.set, pc, k, ltab, u, [&](double* cj_out, double* sj_out, double* ej_out) {
+    if (exact) {
+      fm::sincos_(u * W.set.mu, &js.sj, &js.cj);
+      js.ej = jump_gauss(W.set, u, ltab);
+      js.rho = fm::exp_tab_neg(-(jump_alpha(pc, W.set.hsj2) * (double)(64 * k + 1024)), ltab);
+    } else {
+      js.ej *= js.rho; js.rho *= jrot[2];
+      rotate(js.cj, js.sj, jrot[0], jrot[1]);
+    }
+    *cj_out = js.cj; *sj_out = js.sj; *ej_out = js.ej;
+  });
+  t.G = (k < n_cos) ? t.G : 0.0;                         // ragged last block: every coefficient is a multiple of G
+  KCoef c = make_kcoef(t, pc, k);
+  c.a1 = (k < n_cos) ? c.a1 : 0.0; c.a2 = (k < n_cos) ? c.a2 : 0.0;
   a1 += c.a1; a2 += c.a2; a3 += c.P;
   if (k0 == 0) g0 = __shfl_sync(kFullMask, c.g0, 0);
   __syncwarp();                                        // the previous block's coefficients have been consumed
@@ -122,9 +146,10 @@ __device__ __forceinline__ void dense_pass(DenseWarp& W, int cnt, int n_cos, int
                                            const fm::Tables* __restrict__ ltab) {
   const PassConsts& pc = W.pass;
   double a1 = 0.0, a2 = 0.0, a3 = 0.0, g0 = 0.0;
+  JumpState js;
 #pragma unroll 1
   for (int k0 = 0; k0 < n_cos; k0 += 32) {
-    dense_coefficients(W, pc, k0, n_cos, lane, ltab, a1, a2, a3, g0);
+    dense_coefficients(W, pc, W.jrot, js, k0, n_cos, lane, ltab, a1, a2, a3, g0);
     const double u0 = u_of_k(pc, k0);                   // frequency of the block's first term
     // two strikes per lane and trip (t, t + 32) while both exist, then single strikes: the pair shares the
     // coefficient loads and gives the pipe two independent chains
@@ -160,13 +185,16 @@ __device__ __forceinline__ void dense_pass_single(DenseWarp& W, int t, int n_cos
   if (lane == 0) {
     W.extra_pass = make_pass_consts(W.set, py_min(W.a0, W.x[t] - 0.1), py_max(W.b0, W.x[t] + 0.1), W.pass.T);
     fm::sincos_(u_one(W.extra_pass) * (W.x[t] - W.extra_pass.a), &W.extra_sth, &W.extra_cth);
+    jump_rotation(W.extra_pass, W.set.mu, &W.extra_jrot[0], &W.extra_jrot[1]);
+    W.extra_jrot[2] = fm::exp_neg(-2048.0 * jump_alpha(W.extra_pass, W.set.hsj2));
   }
   __syncwarp();
   const PassConsts& pc = W.extra_pass;
   double a1 = 0.0, a2 = 0.0, a3 = 0.0, g0 = 0.0, acc = 0.0;
+  JumpState js;
 #pragma unroll 1
   for (int k0 = 0; k0 < n_cos; k0 += 32) {
-    dense_coefficients(W, pc, k0, n_cos, lane, ltab, a1, a2, a3, g0);
+    dense_coefficients(W, pc, W.extra_jrot, js, k0, n_cos, lane, ltab, a1, a2, a3, g0);
     double val = 0.0;
     if (lane < 4) {
       double sn, cs, spq, sr;
