@@ -326,7 +326,7 @@ def test_full_size_c2_properties(ctx):
 
 
 def test_host_path_chunking_and_memory_kinds(ctx):
-    """The host-buffer entry points stream chunks of <= 131 072 sets through two slots: results must not depend
+    """The host-buffer entry points stream chunks of <= 131 072 sets through three slots: results must not depend
     on chunk boundaries, on per-set strikes / spots being present, or on the caller's memory being pinned."""
     import torch
     rng = np.random.default_rng(12)
