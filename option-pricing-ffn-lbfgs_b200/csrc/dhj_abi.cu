@@ -736,7 +736,7 @@ static int run_loss(dhj_ctx* ctx, const dhj_market* mk, const double* x, const i
     DHJ_CUDA(ctx, cudaGetLastError());
     PriceArgs pa;
     pa.params = (const double*)ctx->d_xv.p; pa.S0 = (const double*)mk->d_S0.p; pa.s0_stride = 1;
-    pa.row_index = (const int*)ctx->d_idx.p; pa.P = n_units; pa.transform = 1; pa.out = (double*)ctx->d_prices.p;
+    pa.row_index = (const int*)ctx->d_idx.p; pa.P = n_units; pa.transform = 0; pa.out = (double*)ctx->d_prices.p;
     ctx->launches++;
     rc = launch_price(ctx, v, pa, mk->book.max_slice, ctx->stream);
     if (rc) return rc;

@@ -65,13 +65,14 @@ DHJ_HD double counter_uniform_open0(uint64_t w) { return (double)((w >> 11) + 1)
 
 #if defined(__CUDACC__)
 
-// Box-Muller pair of (sample i, slot)
+// Box-Muller pair of (sample i, slot).  The library's own branch-free log / sqrt / sincos (dhj_fastmath.cuh, <= 1-2 ulp):
+// with libdevice's the noise epilogue was bound by their instruction count at 2.5 TB/s, 38 % of the HBM rate.
 __device__ __forceinline__ void counter_normal_pair(uint64_t seed, uint64_t i, uint32_t slot, double* z0, double* z1) {
   uint64_t w0, w1;
   counter_words(seed, i, slot, &w0, &w1);
-  const double R = sqrt(-2.0 * log(counter_uniform_open0(w0)));
+  const double R = fm::sqrt_(-2.0 * fm::log_(counter_uniform_open0(w0)));
   double sn, cs;
-  sincospi(2.0 * counter_uniform(w1), &sn, &cs);
+  fm::sincos_(6.283185307179586 * counter_uniform(w1), &sn, &cs);
   *z0 = R * cs; *z1 = R * sn;
 }
 
@@ -151,7 +152,17 @@ __global__ void __launch_bounds__(kGenMarketSamples) k_gen_market(uint64_t seed,
   const int pitch = M | 1;
   const long long base = (long long)blockIdx.x * kGenMarketSamples;
   const int cnt = (int)min((long long)kGenMarketSamples, n - base);
-  for (int e = threadIdx.x; e < cnt * M; e += kGenMarketSamples) rows[(e / M) * pitch + e % M] = model[base * M + e];
+  // element e = tid, tid + 128, ... of the block's cnt x M tile sits at (row, col) = (e / M, e % M): one division per
+  // thread, then (row, col) advance by (128 / M, 128 % M) with a carry
+  const int step_row = kGenMarketSamples / M, step_col = kGenMarketSamples % M;
+  {
+    int row = threadIdx.x / M, col = threadIdx.x - row * M;
+    for (int e = threadIdx.x; e < cnt * M; e += kGenMarketSamples) {
+      rows[row * pitch + col] = model[base * M + e];
+      row += step_row; col += step_col;
+      if (col >= M) { col -= M; ++row; }
+    }
+  }
   __syncthreads();
   if (threadIdx.x < cnt) {
     double* row = rows + threadIdx.x * pitch;
@@ -165,7 +176,7 @@ __global__ void __launch_bounds__(kGenMarketSamples) k_gen_market(uint64_t seed,
         if (m + h < M) {
           const double price = row[m + h];
           const double mk = price + (noise_sd * z[h]) * price;          // synthetic_generator.py:141-142
-          const double rel = (price - mk) / mk;                           // :154
+          const double rel = fm::div(price - mk, mk);                     // :154
           sq += rel * rel;
           row[m + h] = mk;
         }
@@ -173,7 +184,12 @@ __global__ void __launch_bounds__(kGenMarketSamples) k_gen_market(uint64_t seed,
     loss[base + threadIdx.x] = sq / (double)M;                            // :155 (np.mean)
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < cnt * M; e += kGenMarketSamples) market[base * M + e] = rows[(e / M) * pitch + e % M];
+  int row = threadIdx.x / M, col = threadIdx.x - row * M;
+  for (int e = threadIdx.x; e < cnt * M; e += kGenMarketSamples) {
+    market[base * M + e] = rows[row * pitch + col];
+    row += step_row; col += step_col;
+    if (col >= M) { col -= M; ++row; }
+  }
 }
 
 #endif  // __CUDACC__

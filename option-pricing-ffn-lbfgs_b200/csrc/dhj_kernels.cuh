@@ -239,24 +239,33 @@ __global__ void __launch_bounds__(kBatchThreads, DHJ_BATCH_MINB) k_loss_batch(Sl
   }
 }
 
-// General loss path (slices with more than 8 strikes or more than 32 slices): k_fd_expand builds the stencil
-// points, k_price_dense prices them (transform on), k_loss_reduce forms the losses and gradients.
+// General loss path (slices with more than 8 strikes or more than 32 slices, or a large batch): k_fd_expand builds the
+// stencil points and transforms them to model parameters ONCE per loss evaluation (exp / tanh of the calibrator; the
+// pricing kernel then runs without its per-item transform), k_price_batch / k_price_dense price them, k_loss_reduce
+// forms the losses and gradients.
 __global__ void k_fd_expand(const double* __restrict__ x, const int* __restrict__ market_index, long long n_x, int fd,
-                            double h, double* __restrict__ xv, int* __restrict__ row_index) {
+                            double h, double* __restrict__ pv, int* __restrict__ row_index) {
   const long long unit = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int per = fd ? kFdPoints : 1;
   if (unit >= n_x * per) return;
   const long long c = unit / per;
   const int var = (int)(unit - c * per);
+  double xv[kNumParams];
+#pragma unroll
   for (int i = 0; i < kNumParams; ++i) {
     const double xi = x[kNumParams * c + i];
-    xv[kNumParams * unit + i] = (var == i + 1) ? xi + h : xi;
+    xv[i] = (var == i + 1) ? xi + h : xi;          // scipy's forward point x_i + h
   }
+  const Params m = transform_params(xv);
+  double* out = pv + kNumParams * unit;
+  out[0] = m.v0[0]; out[1] = m.kappa[0]; out[2] = m.theta[0]; out[3] = m.sigma[0]; out[4] = m.rho[0];
+  out[5] = m.v0[1]; out[6] = m.kappa[1]; out[7] = m.theta[1]; out[8] = m.sigma[1]; out[9] = m.rho[1];
+  out[10] = m.lam; out[11] = m.mu; out[12] = m.sj;
   row_index[unit] = market_index ? market_index[c] : 0;
 }
 
 // (options are visited in slice order, pos[i], exactly as k_loss_batch does: the two paths give the same bits)
-__global__ void k_loss_reduce(const double* __restrict__ prices, const double* __restrict__ xv,
+__global__ void k_loss_reduce(const double* __restrict__ prices, const double* __restrict__ pv,
                               const int* __restrict__ row_index, const double* __restrict__ market,
                               const int* __restrict__ pos, int M,
                               long long n_x, int fd, double h, const double* __restrict__ x,
@@ -278,7 +287,7 @@ __global__ void k_loss_reduce(const double* __restrict__ prices, const double* _
       const double rel = (price - mk[o]) / mk[o];
       sq += rel * rel;
     }
-    const Params m = transform_params(xv + kNumParams * unit);
+    const Params m = load_params(pv + kNumParams * unit);
     const double loss = bad ? kSentinel : sq / (double)M + feller_penalty(m);
     f_all[unit] = loss;
     if (fd) {
