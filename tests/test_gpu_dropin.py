@@ -104,8 +104,9 @@ def test_calibrate_c1(mods, golden):
     # somewhere in that spread; the meaningful per-evaluation statement is test_trajectory_replay.
     ens = golden("calib_ensemble.npz")
     print("reference ulp-perturbation ensemble:", sorted(ens["fun"]), "nit", sorted(ens["nit"]))
-    assert res.final_loss <= 1.01 * ens["fun"].max()
-    assert res.final_loss <= 1.01 * max(ref_best, ens["fun"].max())
+    # two-sided: the best of three starts ends inside the reference's own spread (start 1 decides it; the per-start and
+    # per-basin statements are tests/test_gpu_configs.py::test_final_loss_reproducible_starts / _ensemble_two_sided)
+    assert 0.9 * ens["fun"].min() <= res.final_loss <= 1.01 * max(ref_best, ens["fun"].max())
     assert set(res.parameters) == set(c.param_names) and res.model_prices.shape == (15,)
     assert np.abs(res.model_prices - res.market_prices).max() / res.market_prices.max() < 0.01
     assert res.calibration_time <= wall and res.success in (True, False)
