@@ -58,6 +58,19 @@ DHJ_FM double from_hilo(int hi, int lo) {
   uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &b, 8); return x;
 #endif
 }
+// Comparisons on the INTEGER pipe.  Time on this path follows the FP64 instruction count (profiles/README.md r02), and
+// a DSETP holds an FP64 issue slot like a DFMA: where a comparison only needs the sign or the order of two
+// non-negative numbers, the bit patterns say the same.  sign_bit(-0.0) and sign_bit(-NaN) are true; callers note why
+// that is harmless where they use it.
+DHJ_FM bool sign_bit(double x) { return hi32(x) < 0; }
+DHJ_FM bool gt_nonneg(double a, double b) {            // a > b for a, b >= 0 (a NaN orders above everything)
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(a) > __double_as_longlong(b);
+#else
+  int64_t ia, ib; memcpy(&ia, &a, 8); memcpy(&ib, &b, 8); return ia > ib;
+#endif
+}
+
 // x with its sign bit xor-ed with bit 31 of `signmask`
 DHJ_FM double xor_sign(double x, int signmask) { return from_hilo(hi32(x) ^ (signmask & (int)0x80000000), lo32(x)); }
 
@@ -282,6 +295,8 @@ static const Tables kTables = {{
 }};
 
 // e_off: returns log(w * 2^e_off) (the offset merges with the exponent bias: free)
+// NAN_GUARD = false drops the final `+ (w - w)` (2 FP64 instructions): for callers whose result is NaN anyway when w is.
+template <bool NAN_GUARD = true>
 DHJ_FM double log_tab(double w, const Tables* __restrict__ tab, int e_off = 0) {
   const int hi = hi32(w);
   const int e = ((hi >> 20) & 0x7ff) - 1023 + e_off;
@@ -296,7 +311,7 @@ DHJ_FM double log_tab(double w, const Tables* __restrict__ tab, int e_off = 0) {
   const double ef = (double)e;
   // ln 2 - Ln2HiFull rounded to a high word (32-bit immediate): the 21-bit constant misses 1e-23 |e|
   const double res = fma(ef, kS.Ln2HiFull, t.l) + fma(ef, 2.31904650766222601363e-17, l1p);
-  return res + (w - w);                     // NaN or inf in -> NaN out (the bit surgery above would launder them)
+  return NAN_GUARD ? res + (w - w) : res;   // NaN or inf in -> NaN out (the bit surgery above would launder them)
 }
 
 // ---- table-driven exp ------------------------------------------------------------------------------
@@ -328,6 +343,13 @@ DHJ_FM double exp_tab(double x, const Tables* __restrict__ tab) {
 DHJ_FM double exp_tab_neg(double x, const Tables* __restrict__ tab) {
   const double res = exp_tab_core(x, tab);
   return (x < -708.0) ? 0.0 : res;
+}
+// the same with the underflow test on the integer pipe: the high word of a double below -708 is, as an unsigned
+// number, above that of -708.0 (0xC0862000); -inf flushes to 0 as it must, and so does a NEGATIVE NaN — for callers
+// whose result is NaN anyway when x is
+DHJ_FM double exp_tab_neg_ix(double x, const Tables* __restrict__ tab) {
+  const double res = exp_tab_core(x, tab);
+  return ((unsigned)hi32(x) > 0xC0862000u) ? 0.0 : res;
 }
 
 // ---- atan2 -----------------------------------------------------------------------------------------
@@ -370,7 +392,7 @@ DHJ_FM double atan2_nz(double y, double x) { return atan2_impl<false>(y, x); }
 template <bool ZERO_OK>
 DHJ_FM double atan2_tab_impl(double y, double x, const Tables* __restrict__ tab) {
   const double ax = fabs(x), ay = fabs(y);
-  const bool steep = ay > ax;
+  const bool steep = gt_nonneg(ay, ax);             // integer compare; a NaN operand lands in mx or mn either way
   const double mx = steep ? ay : ax, mn = steep ? ax : ay;
   const double tt = fma(mn, rcp_seed(mx), kS.AtanMagic);
   unsigned i = (unsigned)lo32(tt);
@@ -382,7 +404,8 @@ DHJ_FM double atan2_tab_impl(double y, double x, const Tables* __restrict__ tab)
   const double p = fma(z, fma(z, -0.14285719394683837891, kS.AtC2), kS.AtC1);   // -1/7 as a high word: immediate
   double r = tab->atan64[i] + fma(t * z, p, t);     // atan(mn/mx) in [0, pi/4]
   r = steep ? kS.PiO2 - r : r;
-  r = (x < 0.0) ? kS.PiD - r : r;
+  // sign bit instead of x < 0: differs for x = -0.0 only, where r = pi/2 exactly and pi - pi/2 = pi/2 exactly
+  r = sign_bit(x) ? kS.PiD - r : r;
   if (ZERO_OK) r = (mx == 0.0) ? ((x < 0.0 || (x == 0.0 && signbit(x))) ? kS.PiD : 0.0) : r;
   return copysign(r, y);
 }

@@ -206,7 +206,7 @@ DHJ_HD void heston_factor(const SetConsts& s, int j, double u, double T, const f
   // selects and two sign operations per factor and k)
   double dr = t, di = other;
 #if defined(__CUDA_ARCH__)
-  if (__any_sync(__activemask(), zr < 0.0))
+  if (__any_sync(__activemask(), fm::sign_bit(zr)))      // (sign bit: an integer test; -0.0 takes the general branch too)
 #endif
   {
     const bool pos = !(zr < 0.0);
@@ -214,7 +214,8 @@ DHJ_HD void heston_factor(const SetConsts& s, int j, double u, double T, const f
     di = pos ? other : copysign(t, zi);
   }
   // E = exp(-d T)
-  const double er = fm::exp_tab_neg(-dr * T, ltab);
+  // (integer underflow test: if -dr T is NaN so is beta - d, and with it D and the factor's whole contribution)
+  const double er = fm::exp_tab_neg_ix(-dr * T, ltab);
   double sn, cs;
   fm::sincos_(-di * T, &sn, &cs);
   const double Er = er * cs, Ei = er * sn;
@@ -234,7 +235,8 @@ DHJ_HD void heston_factor(const SetConsts& s, int j, double u, double T, const f
   xbr = fma(Mr, g, xbr);
   xbi = fma(Mi, g, xbi);
   // A = c (m T - 2 log(D/(2d))):  -2 log|D/(2d)| = log(4 |z| / |D|^2), |d|^2 = |z| = h;  argument from D*conj(d)
-  const double L = fm::log_tab(h * inD, ltab, 2);
+  // (no NaN guard: a NaN h or 1/|D|^2 already makes B_j v0_j, hence the exponent and the price, NaN)
+  const double L = fm::log_tab<false>(h * inD, ltab, 2);
   const double li = fm::atan2_tab_nz(fma(Di, dr, -(Dr * di)), fma(Dr, dr, Di * di), ltab);
   const double cT = s.c[j] * T;
   aR = fma(s.c[j], L, aR);
