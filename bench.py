@@ -102,11 +102,12 @@ def gen_params(P: int, seed: int) -> np.ndarray:
 
 
 def kernel_source_sha() -> str:
-    """sha256 over the kernel sources: ties profiles/ncu_summary.json to the build it was captured from."""
+    """sha256 over the DEVICE sources (kernels, device math, tables; not the host side of the ABI): ties
+    profiles/ncu_summary.json to the build it was captured from."""
     h = hashlib.sha256()
     csrc = os.path.join(PKG, "csrc")
     for f in sorted(os.listdir(csrc)):
-        if f.endswith((".cuh", ".cu", ".inc")):
+        if f.endswith((".cuh", ".inc")):
             h.update(f.encode())
             h.update(open(os.path.join(csrc, f), "rb").read())
     return h.hexdigest()[:16]
