@@ -170,6 +170,26 @@ struct dhj_ctx {
   PinBuf h_x, h_res;
   size_t counters_zeroed = 0;
   DevBuf d_peak;
+  // device buffers of destroyed markets, kept for the next dhj_market_create: cudaMalloc / cudaFree synchronise the
+  // whole device, which stalls the other lock-step pipelines of a calibrate_many call every time a market comes or goes
+  std::vector<DevBuf> pool;
+  cudaError_t pool_take(DevBuf* out, size_t bytes) {
+    int best = -1;
+    for (size_t i = 0; i < pool.size(); ++i)
+      if (pool[i].cap >= bytes && (best < 0 || pool[i].cap < pool[(size_t)best].cap)) best = (int)i;
+    if (best >= 0 && pool[(size_t)best].cap <= 4 * std::max(bytes, (size_t)4096)) {
+      *out = pool[(size_t)best];
+      pool.erase(pool.begin() + best);
+      return cudaSuccess;
+    }
+    *out = DevBuf();
+    return out->reserve(bytes);
+  }
+  void pool_give(DevBuf* b) {
+    if (b->p && pool.size() < 32 && b->cap <= ((size_t)256 << 20)) pool.push_back(*b);
+    else b->release();
+    b->p = nullptr; b->cap = 0;
+  }
 };
 
 struct dhj_market {
@@ -542,6 +562,8 @@ int dhj_destroy(dhj_ctx* ctx) {
   ctx->d_x.release(); ctx->d_xv.release(); ctx->d_idx.release(); ctx->d_f.release(); ctx->d_fg.release();
   ctx->d_counters.release(); ctx->d_prices.release(); ctx->h_x.release(); ctx->h_res.release();
   ctx->d_peak.release();
+  for (DevBuf& b : ctx->pool) b.release();
+  ctx->pool.clear();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return DHJ_OK;
@@ -648,10 +670,10 @@ int dhj_market_create(dhj_ctx* ctx, int32_t n_markets, int32_t M, const double* 
   mk->book.pack(image.data());
   const size_t kbytes = (size_t)(strike_stride ? n_markets : 1) * M * sizeof(double);
   const size_t pbytes = (size_t)n_markets * M * sizeof(double);
-  cudaError_t e = mk->d_book.reserve(bb);
-  if (e == cudaSuccess) e = mk->d_strike.reserve(kbytes);
-  if (e == cudaSuccess) e = mk->d_S0.reserve((size_t)n_markets * sizeof(double));
-  if (e == cudaSuccess) e = mk->d_price.reserve(pbytes);
+  cudaError_t e = ctx->pool_take(&mk->d_book, bb);
+  if (e == cudaSuccess) e = ctx->pool_take(&mk->d_strike, kbytes);
+  if (e == cudaSuccess) e = ctx->pool_take(&mk->d_S0, (size_t)n_markets * sizeof(double));
+  if (e == cudaSuccess) e = ctx->pool_take(&mk->d_price, pbytes);
   if (e == cudaSuccess) e = cudaMemcpy(mk->d_book.p, image.data(), bb, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(mk->d_strike.p, strike, kbytes, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(mk->d_S0.p, S0, (size_t)n_markets * sizeof(double), cudaMemcpyHostToDevice);
@@ -671,8 +693,16 @@ int dhj_market_create(dhj_ctx* ctx, int32_t n_markets, int32_t M, const double* 
 
 int dhj_market_destroy(dhj_market* mk) {
   if (!mk) return DHJ_OK;
-  if (mk->ctx) cudaSetDevice(mk->ctx->device);
-  mk->d_book.release(); mk->d_strike.release(); mk->d_S0.release(); mk->d_price.release();
+  if (mk->ctx) {
+    cudaSetDevice(mk->ctx->device);
+    // launches that read the market's tables are all on the context's stream: once it has drained the buffers can
+    // serve the next market
+    cudaStreamSynchronize(mk->ctx->stream);
+    mk->ctx->pool_give(&mk->d_book); mk->ctx->pool_give(&mk->d_strike);
+    mk->ctx->pool_give(&mk->d_S0); mk->ctx->pool_give(&mk->d_price);
+  } else {
+    mk->d_book.release(); mk->d_strike.release(); mk->d_S0.release(); mk->d_price.release();
+  }
   delete mk;
   return DHJ_OK;
 }
