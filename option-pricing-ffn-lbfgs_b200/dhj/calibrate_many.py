@@ -195,7 +195,10 @@ def _calibrate_pipelined(spots, risk_free_rate, strikes, maturities, is_call, pr
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    set_host_threads(max(1, cores // n_pipes))             # the pipelines' ask / tell loops share the cores
+    # the pipelines' ask / tell loops share this process's part of the host's cores (torchrun's LOCAL_WORLD_SIZE ranks
+    # share the host: 2 ranks x 6 pipelines x 5 threads on 32 cores ran 0.68 s where 0.36 s is possible)
+    ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    set_host_threads(max(1, cores // (n_pipes * ranks_here)))
     threads = [threading.Thread(target=work, args=(i,)) for i in range(n_pipes)]
     try:
         for t in threads:
