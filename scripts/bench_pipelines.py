@@ -21,7 +21,7 @@ K = np.tile(np.array(GRID_K)[None, :] * spots[:, None] / 100.0, (1, 3)); T = np.
 np.random.seed(1)
 x0 = dhj.initial_guesses(spots, K, T, market, 3)
 ref = None
-for pipes in (1, 2, 3, 4, 6):
+for pipes in (1, 2, 3, 4, 6, 8):
     dhj.calibrate_many(spots, 0.03, K, T, np.ones(15), market, maxiter=3, multi_start=3, x0=x0, pipelines=pipes)
     best = 1e9
     for rep in range(3):
