@@ -270,6 +270,57 @@ def test_c4_shards_do_not_depend_on_the_split(ctx):
     assert abs((whole["market"] / whole["model"] - 1.0).std() - 0.02) < 2e-4
 
 
+def test_c4_full_size_properties(ctx):
+    """BASELINE config C4 at FULL size on one GPU: 100 M samples x 15 options drawn, priced, noised and reduced to
+    losses on the device (36 GB resident), judged through size-independent properties — determinism of the whole sweep,
+    ranges, history structure, monotonicity of every price row, noise statistics — and the oracle on samples scattered
+    over the whole index range (each drawn from its history's start by the oracle's restatement of the stream)."""
+    import torch
+    n, M = 100_000_000, 15
+    dev = torch.device("cuda", 0)
+    free, _ = torch.cuda.mem_get_info(dev)
+    if free < 80 * 2 ** 30:
+        pytest.skip("needs 80 GB of free device memory")
+    f64 = dict(dtype=torch.float64, device=dev)
+    bufs = {k: torch.empty(s, **f64) for k, s in (("params", (n, 13)), ("spots", (n,)), ("model", (n, M)),
+                                                  ("market", (n, M)), ("loss", (n,)))}
+    args = [GEN[k] for k in ("path_len", "lo", "hi", "persistence", "spot0", "ret_mean", "ret_sd", "noise_sd",
+                             "strikes_rel", "maturities", "r")]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def sweep():
+        ctx.generate_dev(7, 0, n, *args, bufs["params"].data_ptr(), bufs["spots"].data_ptr(), bufs["model"].data_ptr(),
+                         bufs["market"].data_ptr(), bufs["loss"].data_ptr(), stream)
+        torch.cuda.synchronize()
+        return [float(bufs[k].sum().item()) for k in ("params", "spots", "model", "market", "loss")]
+
+    t0 = time.perf_counter()
+    sums = sweep()
+    wall = time.perf_counter() - t0
+    assert sums == sweep()                                                # the whole sweep is deterministic
+    print("C4 full size: %d samples in %.2f s incl. checksums; mean loss %.4e" % (n, wall, sums[4] / n))
+    model, market = bufs["model"].view(n, 3, 5), bufs["market"]
+    assert bool(torch.isfinite(model).all()) and bool((model > 0).all()) and bool(torch.isfinite(market).all())
+    assert bool((model[:, :, 1:] < model[:, :, :-1]).all())               # decreasing in strike, every sample
+    assert bool((model[:, 1:, :] > model[:, :-1, :]).all())               # increasing in maturity
+    lo_t, hi_t = torch.tensor(GEN["lo"], **f64), torch.tensor(GEN["hi"], **f64)
+    assert bool((bufs["params"] >= lo_t).all()) and bool((bufs["params"] <= hi_t).all())
+    assert bool((bufs["spots"][::500] == 100.0).all())                    # every history restarts at spot0
+    noise = market / bufs["model"] - 1.0
+    assert abs(float(noise.std().item()) - 0.02) < 1e-5 and abs(float(noise.mean().item())) < 1e-5
+    assert abs(sums[4] / n - 4e-4) < 2e-6                                 # E[loss] = noise_sd^2 to first order
+    # scattered samples against the oracle (each needs its history's prefix: whole histories are compared)
+    for q in (0, 1, 77_777, 199_999):                                     # first, second, a middle and the last history
+        lo_i = q * 500
+        want = O.counter_generate(7, lo_i, 500, 500)
+        got = {k: bufs[k][lo_i:lo_i + 500].cpu().numpy() for k in ("params", "spots", "model", "market", "loss")}
+        assert np.abs(got["params"] - want["params"]).max() <= 1e-15
+        assert rel_err(got["spots"], want["spots"]).max() <= 1e-13
+        assert rel_err(got["model"], want["model"]).max() <= PRICE_RTOL
+        assert rel_err(got["market"], want["market"]).max() <= PRICE_RTOL
+        assert np.abs(got["loss"] - want["loss"]).max() <= LOSS_ATOL
+
+
 def test_c4_sharded_generator_api(mods, tmp_path):
     """generate_synthetic_arrays(seed=..., sharded=True): one process = one shard = the whole dataset; the written
     shard loads back as a lazy CalibrationResult view with the reference's field layout."""
