@@ -90,6 +90,29 @@ def test_c3_full_shape_edge(ctx):
     assert rel_err(got[sel], want)[want >= 0.1].max() <= PRICE_RTOL
 
 
+def test_c3_surface_as_fd_gradient_batch(ctx):
+    """BASELINE configs[2] calls the dense surface the "FD-gradient batch shape": a calibration against the whole
+    200 x 20 surface (4 000 options) asks for f and 13 forward differences per optimiser state.  16 states = 224 loss
+    evaluations = 896 000 prices through expand -> dense pricing kernel -> reduce, every loss against the C oracle
+    (N = 128: the reference's loss always prices with the default N, lbfgs_calibrator.py:150)."""
+    rng = np.random.default_rng(20260107)
+    Ks, Ts = np.linspace(80.0, 120.0, 200), np.linspace(0.25, 2.0, 20)
+    K, T = np.tile(Ks, 20), np.repeat(Ts, 200)
+    truth = _c3_params()[0]
+    market = O.c_price_batch(truth, 100.0, K, T, np.ones(K.size), 0.03)[0] * (1 + 0.02 * rng.standard_normal(K.size))
+    mk = ctx.market(100.0, 0.03, K, T, np.ones(K.size), market)
+    x = O.inverse_transform_params(truth)[None, :] + 0.05 * rng.standard_normal((16, 13))
+    f, g, f_all = mk.loss_fd(x, 1e-8, want_all=True)
+    pts = np.concatenate([O.fd_stencil(x[c])[0] for c in range(16)])
+    want = O.c_loss_batch(pts, 100.0, 0.03, K, T, np.ones(K.size), market).reshape(16, 14)
+    print("surface loss: max abs err %.3e over 224 evaluations of a 4 000-option market" % np.abs(f_all - want).max())
+    assert np.abs(f_all - want).max() <= LOSS_ATOL
+    assert np.array_equal(f, f_all[:, 0])
+    for c in range(16):
+        assert np.array_equal(g[c], (f_all[c, 1:] - f_all[c, 0]) / ((x[c] + 1e-8) - x[c]))
+    mk.close()
+
+
 # ---- loss parity away from the noise-free C1 trajectory ----------------------------------------------------------
 def test_noisy_market_trajectory_replay(ctx, golden):
     """Every x the REFERENCE optimiser evaluated on 4 noisy generator-style markets, starts 0 and 2 (7 056 loss
